@@ -1,0 +1,870 @@
+// abi.cu -- C ABI of libgomelcuda.so (include/gomel_cuda.h): context, tables, launch logic.
+// No PyTorch, no cuFFT, no CPU fallback: every transform below is one of the kernels in
+// kernels.cuh.  Host code here only sizes, stages and launches.
+#include "../../include/gomel_cuda.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace gomel;
+
+namespace {
+
+constexpr int kHS = 5;                       // hop slots: Window / 256 = 1280 / 256
+constexpr int kHop = 256 * kHS;
+constexpr int kHalo = (16 - kHS) * 256;      // Resolut - Window = 2816 samples shared by adjacent tiles
+
+enum Scratch { S_F64IN = 0, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_F32C, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
+               S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_COUNT };
+
+}  // namespace
+
+struct gomel_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
+    float4* d_tables = nullptr;
+    // mel tables
+    int tbl_mels = 0;
+    int *d_fwd_lo = nullptr, *d_fwd_hi = nullptr, *d_inv_lo = nullptr, *d_inv_hi = nullptr;
+    float* d_fwd_mod = nullptr;
+    double* d_inv_mod = nullptr;
+    // phase gain tables
+    float *d_gain_head = nullptr, *d_gain_mid = nullptr, *d_gain_tail = nullptr;
+    long gain_frames_key = -1; double gain_boost_key = 0; int gain_head_len = 0, gain_tail_len = 0;
+    void* scratch[S_COUNT] = {};
+    size_t scratch_cap[S_COUNT] = {};
+    unsigned long long launches = 0;
+    int tile_override = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+int fail(gomel_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? GOMEL_E_NOMEM : GOMEL_E_CUDA,         \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+    } while (0)
+
+int ensure(gomel_ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (ctx->scratch_cap[slot] < bytes) {
+        if (ctx->scratch[slot]) { CU(cudaStreamSynchronize(ctx->st)); CU(cudaFree(ctx->scratch[slot])); }
+        ctx->scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0;
+        size_t cap = bytes + (bytes >> 3) + 256;
+        CU(cudaMalloc(&ctx->scratch[slot], cap));
+        ctx->scratch_cap[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return 0;
+}
+
+int check_cfg(gomel_ctx* ctx, const gomel_config* cfg)
+{
+    if (!cfg) return fail(ctx, GOMEL_E_ARG, "config is NULL");
+    if (cfg->n_fft != kN || cfg->hop != kHop)
+        return fail(ctx, GOMEL_E_UNSUPPORTED, "this build supports Resolut=4096, Window=1280 only");
+    return 0;
+}
+
+long pad_len(long n, int filter)            // mel/impl.go:429-455
+{
+    const long min_target = 15L * filter;
+    long pad = 0;
+    if (n >= min_target) { const long rem = (n - min_target) % filter; if (rem) pad = filter - rem - 1; }
+    else pad = min_target - n - 1;
+    return pad > 0 ? pad : 0;
+}
+
+Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len)
+{
+    Tiling tl;
+    tl.n_frames = (int)n_frames;
+    int T;
+    if (ctx->tile_override > 0) T = ctx->tile_override;
+    else {
+        const long slots = 2L * ctx->sm_count;
+        long tiles_wanted = (8 * slots + n_clips - 1) / n_clips;
+        if (tiles_wanted < 1) tiles_wanted = 1;
+        T = (int)((n_frames + tiles_wanted - 1) / tiles_wanted);
+        if (T < 16) T = 16;
+    }
+    if (T & 1) T++;
+    if (T < 4) T = 4;
+    const long fr_even = n_frames + (n_frames & 1);
+    if (T > fr_even) T = (int)fr_even;
+    if (T < 4) T = 4;
+    tl.tile_frames = T;
+    tl.n_tiles = (int)((n_frames + T - 1) / T);
+    tl.sig_stride = sig_stride;
+    tl.sig_len = sig_len;
+    return tl;
+}
+
+int grid_1d(long n, int block) { long g = (n + block - 1) / block; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
+
+void build_fft_tables(std::vector<float>& blob)
+{
+    blob.assign(kTableBytes / 4, 0.0f);
+    float* T1 = blob.data();
+    float* T2 = T1 + kT1Cells * 2;
+    float* win = T2 + kT2Cells * 2;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k0 = 1; k0 < 16; k0++)
+        for (int t = 0; t < 256; t++) {
+            const double a = two_pi * (double)((t * k0) % 4096) / 4096.0;
+            T1[((k0 - 1) * 256 + t) * 2 + 0] = (float)std::cos(a);
+            T1[((k0 - 1) * 256 + t) * 2 + 1] = (float)(-std::sin(a));
+        }
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int n0 = 0; n0 < 16; n0++) {
+            const double a = two_pi * (double)((n0 * k1) % 256) / 256.0;
+            T2[(k1 * 16 + n0) * 2 + 0] = (float)std::cos(a);
+            T2[(k1 * 16 + n0) * 2 + 1] = (float)(-std::sin(a));
+        }
+    // symmetric Hann of gossp/go-dsp: 0.5*(1-cos(2 pi n/(N-1)))  (phase.py:122 np.hanning)
+    for (int m = 0; m < 16; m++)
+        for (int t = 0; t < 256; t++) {
+            const int n = t + 256 * m;
+            win[m * 256 + t] = (float)(0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1))));
+        }
+}
+
+template <typename K>
+int set_smem_attr(gomel_ctx* ctx, K kernel)
+{
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return 0;
+}
+
+// ---- window-sum gain tables for phase.ISTFT (phase/phase.go:114-130), float64 on the host
+int prepare_gain(gomel_ctx* ctx, long n_frames, double boost)
+{
+    const long key = n_frames <= 16 ? n_frames : 17;
+    if (ctx->gain_frames_key == key && ctx->gain_boost_key == boost && ctx->d_gain_head) return 0;
+    const long F = n_frames <= 16 ? n_frames : 16;
+    const long ola = kN + (F - 1) * kHop;
+    std::vector<double> w(kN), ws(ola, 0.0);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int n = 0; n < kN; n++) w[n] = 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1)));
+    for (long f = 0; f < F; f++)
+        for (int j = 0; j < kN; j++) ws[f * kHop + j] += w[j] * w[j];
+    double mx = 0.0;
+    for (long i = 0; i < ola; i++) if (ws[i] > mx) mx = ws[i];
+    const double thr = mx * 0.5;
+    auto gain = [&](double v) -> float {
+        double g = 1.0;
+        if (v > thr) g = 1.0 / v;
+        else if (v > 1e-21) g = 1.0 / thr;
+        if (boost != 0) g *= boost;
+        return (float)g;
+    };
+    std::vector<float> head, mid(kHop, 1.0f), tail;
+    if (n_frames <= 16) {
+        head.resize(ola);
+        for (long i = 0; i < ola; i++) head[i] = gain(ws[i]);
+        ctx->gain_head_len = (int)ola; ctx->gain_tail_len = 0;
+        tail.assign(1, 1.0f);
+    } else {
+        head.resize(kN); tail.resize(kN);
+        for (int i = 0; i < kN; i++) { head[i] = gain(ws[i]); tail[i] = gain(ws[ola - kN + i]); }
+        for (long s = kN; s < kN + kHop; s++) mid[s % kHop] = gain(ws[s]);
+        ctx->gain_head_len = kN; ctx->gain_tail_len = kN;
+    }
+    if (ctx->d_gain_head) { CU(cudaStreamSynchronize(ctx->st)); cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail); }
+    ctx->d_gain_head = ctx->d_gain_mid = ctx->d_gain_tail = nullptr;
+    CU(cudaMalloc(&ctx->d_gain_head, head.size() * 4));
+    CU(cudaMalloc(&ctx->d_gain_mid, mid.size() * 4));
+    CU(cudaMalloc(&ctx->d_gain_tail, tail.size() * 4));
+    CU(cudaMemcpyAsync(ctx->d_gain_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_gain_mid, mid.data(), mid.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->d_gain_tail, tail.data(), tail.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->gain_frames_key = key; ctx->gain_boost_key = boost;
+    return 0;
+}
+
+// ---- unlocked device-level implementations ---------------------------------------------
+int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_sig, int n_clips, long sig_stride,
+            long sig_len, long n_frames, float* d_out)
+{
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!d_sig || !d_out || n_clips <= 0 || n_frames <= 0 || sig_stride < sig_len)
+        return fail(ctx, GOMEL_E_ARG, "bad argument to forward transform");
+    if (sig_len < kN + (n_frames - 1) * (long)kHop)
+        return fail(ctx, GOMEL_E_ARG, "signal shorter than the frames requested");
+    FwdParams p = {};
+    p.sig = d_sig; p.tables = ctx->d_tables;
+    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, sig_len);
+    if (mode == MODE_MEL) {
+        if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
+            return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
+        p.fwd_lo = ctx->d_fwd_lo; p.fwd_hi = ctx->d_fwd_hi; p.fwd_mod = ctx->d_fwd_mod; p.n_mels = cfg->n_mels;
+        p.mel_out = d_out;
+    } else if (mode == MODE_PHASE) {
+        if (cfg->n_freqs <= 0 || cfg->n_freqs > kN / 2) return fail(ctx, GOMEL_E_ARG, "NumFreqs out of range");
+        p.n_freqs = cfg->n_freqs; p.phase_out = reinterpret_cast<float2*>(d_out);
+    } else {
+        p.spec_out = reinterpret_cast<float2*>(d_out);
+    }
+    const long grid = (long)n_clips * p.tl.n_tiles;
+    if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
+    CU(cudaEventRecord(ctx->ev_k0, ctx->st));
+    if (mode == MODE_MEL) k_stft_fwd<kHS, MODE_MEL><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+    else if (mode == MODE_PHASE) k_stft_fwd<kHS, MODE_PHASE><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+    else k_stft_fwd<kHS, MODE_SPEC><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+    CU(cudaEventRecord(ctx->ev_k1, ctx->st));
+    ctx->hot_launches = 1;
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_clips, long n_frames,
+           const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
+{
+    const long ola = kN + (n_frames - 1) * (long)kHop;
+    if (sig_stride < ola) return fail(ctx, GOMEL_E_ARG, "sig_stride < ola_len");
+    if (d_init == d_out) return fail(ctx, GOMEL_E_ARG, "d_init and d_out must not alias");
+    const int iters = cfg->gl_iters;
+    if (iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
+    const size_t sig_bytes = (size_t)n_clips * sig_stride * 4;
+    if (!d_init) {
+        void* b; if (int rc = ensure(ctx, S_INIT, sig_bytes, &b)) return rc;
+        k_fill_uniform<<<grid_1d((long)n_clips * sig_stride, 256), 256, 0, ctx->st>>>((float*)b, (long)n_clips * sig_stride, seed);
+        ctx->launches++;
+        d_init = (const float*)b;
+    }
+    if (iters == 0) {       // mel/mel.go:85: zero iterations return the start signal
+        CU(cudaMemcpyAsync(d_out, d_init, sig_bytes, cudaMemcpyDeviceToDevice, ctx->st));
+        return 0;
+    }
+    SynParams p = {};
+    p.tables = ctx->d_tables;
+    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola);
+    p.mags = d_mags;
+    void *tmp = nullptr, *hb[2] = { nullptr, nullptr };
+    if (iters > 1) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &tmp)) return rc; }
+    const size_t hb_bytes = (size_t)n_clips * p.tl.n_tiles * kHalo * 4 + 16;
+    if (int rc = ensure(ctx, S_HB0, hb_bytes, &hb[0])) return rc;
+    if (int rc = ensure(ctx, S_HB1, hb_bytes, &hb[1])) return rc;
+    const long grid = (long)n_clips * p.tl.n_tiles;
+    if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
+    const float* cur = d_init;
+    CU(cudaEventRecord(ctx->ev_k0, ctx->st));
+    for (int i = 0; i < iters; i++) {
+        float* dst = (((iters - 1 - i) & 1) == 0) ? d_out : (float*)tmp;
+        p.sig_in = cur; p.sig_out = dst;
+        p.hb_in = (i == 0) ? nullptr : (const float*)hb[(i - 1) & 1];
+        p.hb_out = (float*)hb[i & 1];
+        k_gl_iter<kHS><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+        ctx->launches++;
+        cur = dst;
+    }
+    CU(cudaEventRecord(ctx->ev_k1, ctx->st));
+    ctx->hot_launches = iters;
+    if (p.tl.n_tiles > 1) {
+        const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;
+        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, kHop, kHalo,
+                                                           n_clips, 0, p);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, float* d_mags)
+{
+    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
+        return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
+    if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
+    long g = n_rows < 148L * 8 ? n_rows : 148L * 8;
+    k_mags_from_mel<T><<<(unsigned)g, 256, (size_t)cfg->n_mels * 2 * sizeof(double), ctx->st>>>(
+        d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int from_mel_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, int n_clips, long n_frames,
+                      const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
+{
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!d_mel || !d_out || n_clips <= 0 || n_frames <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument to from_mel");
+    void* mags;
+    if (int rc = ensure(ctx, S_MAGS, (size_t)n_clips * n_frames * kMagStride * 4, &mags)) return rc;
+    if (int rc = mags_dev<T>(ctx, cfg, d_mel, (long)n_clips * n_frames, (float*)mags)) return rc;
+    return gl_dev(ctx, cfg, (const float*)mags, n_clips, n_frames, d_init, seed, sig_stride, d_out);
+}
+
+int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_spec, int n_clips, long n_frames,
+                        long sig_stride, float* d_out)
+{
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!d_spec || !d_out || n_clips <= 0 || n_frames <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument to from_phase");
+    if (cfg->n_freqs <= 0 || cfg->n_freqs > kN / 2) return fail(ctx, GOMEL_E_ARG, "NumFreqs out of range");
+    const long ola = kN + (n_frames - 1) * (long)kHop;
+    if (sig_stride < ola) return fail(ctx, GOMEL_E_ARG, "sig_stride < ola_len");
+    if (int rc = prepare_gain(ctx, n_frames, cfg->volume_boost)) return rc;
+    SynParams p = {};
+    p.tables = ctx->d_tables;
+    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola);
+    p.sig_out = d_out;
+    p.spec = reinterpret_cast<const float2*>(d_spec); p.n_freqs = cfg->n_freqs;
+    p.gain_head = ctx->d_gain_head; p.gain_mid = ctx->d_gain_mid; p.gain_tail = ctx->d_gain_tail;
+    p.head_len = ctx->gain_head_len; p.tail_len = ctx->gain_tail_len;
+    void* hb;
+    if (int rc = ensure(ctx, S_HB0, (size_t)n_clips * p.tl.n_tiles * kHalo * 4 + 16, &hb)) return rc;
+    p.hb_out = (float*)hb;
+    const long grid = (long)n_clips * p.tl.n_tiles;
+    if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
+    k_istft_phase<kHS><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+    ctx->launches++;
+    if (p.tl.n_tiles > 1) {
+        const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;
+        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb, p.tl, kHop, kHalo, n_clips, 1, p);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+struct Guard {
+    gomel_ctx* c;
+    explicit Guard(gomel_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
+    ~Guard() { c->mu.unlock(); }
+};
+
+}  // namespace
+
+// =================================================================== exported C ABI
+extern "C" {
+
+const char* gomel_version(void) { return "gomel_b200 0.1 (sm_100a, Resolut 4096 / Window 1280)"; }
+
+int gomel_ctx_create(int device, gomel_ctx** out)
+{
+    if (!out) return GOMEL_E_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) return GOMEL_E_CUDA;
+    gomel_ctx* ctx = new gomel_ctx();
+    ctx->device = device;
+    auto boot = [&]() -> int {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ctx->ev0));
+        CU(cudaEventCreate(&ctx->ev1));
+        CU(cudaEventCreate(&ctx->ev_k0));
+        CU(cudaEventCreate(&ctx->ev_k1));
+        std::vector<float> blob;
+        build_fft_tables(blob);
+        CU(cudaMalloc(&ctx->d_tables, kTableBytes));
+        CU(cudaMemcpy(ctx->d_tables, blob.data(), kTableBytes, cudaMemcpyHostToDevice));
+        if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_MEL>)) return rc;
+        if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_PHASE>)) return rc;
+        if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_SPEC>)) return rc;
+        if (int rc = set_smem_attr(ctx, k_gl_iter<kHS>)) return rc;
+        if (int rc = set_smem_attr(ctx, k_istft_phase<kHS>)) return rc;
+        return 0;
+    };
+    const int rc = boot();
+    if (rc) { fprintf(stderr, "gomel_ctx_create: %s\n", ctx->err.c_str()); delete ctx; return rc; }
+    *out = ctx;
+    return 0;
+}
+
+void gomel_ctx_destroy(gomel_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    for (int i = 0; i < S_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
+    cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
+    cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
+    cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st_h2d); cudaStreamDestroy(ctx->st_d2h);
+    delete ctx;
+}
+
+const char* gomel_last_error(gomel_ctx* ctx) { return ctx ? ctx->err.c_str() : "NULL context"; }
+unsigned long long gomel_launch_count(gomel_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gomel_set_tile_frames(gomel_ctx* ctx, int tile_frames)
+{
+    if (!ctx || tile_frames < 0) return GOMEL_E_ARG;
+    ctx->tile_override = tile_frames;
+    return 0;
+}
+
+int gomel_frames(const gomel_config* cfg, long n_samples, long* n_padded, long* n_frames, long* ola_len)
+{
+    if (!cfg || n_samples <= 0 || cfg->hop <= 0 || cfg->n_fft <= 0) return GOMEL_E_ARG;
+    const long np = n_samples + pad_len(n_samples, cfg->hop);
+    if (np < cfg->n_fft) return GOMEL_E_ARG;
+    const long fr = (long)((double)(np - cfg->n_fft) / (double)cfg->hop) + 1;   // gossp NumFrames
+    if (n_padded) *n_padded = np;
+    if (n_frames) *n_frames = fr;
+    if (ola_len) *ola_len = cfg->n_fft + (fr - 1) * (long)cfg->hop;
+    return 0;
+}
+
+long gomel_ola_len(const gomel_config* cfg, long n_frames)
+{
+    if (!cfg || n_frames <= 0) return GOMEL_E_ARG;
+    return cfg->n_fft + (n_frames - 1) * (long)cfg->hop;
+}
+
+int gomel_set_mel_tables(gomel_ctx* ctx, const gomel_config* cfg, const int* fwd_lo, const int* fwd_hi,
+                         const double* fwd_mod, const int* inv_lo, const int* inv_hi, const double* inv_mod)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    const int mels = cfg->n_mels, B = kN / 2;
+    if (mels <= 0 || mels > 4096 || !fwd_lo || !fwd_hi || !fwd_mod || !inv_lo || !inv_hi || !inv_mod)
+        return fail(ctx, GOMEL_E_ARG, "bad mel table arguments");
+    // index ranges the reference would panic on (mel/impl.go:331-338, :366-377) are refused here
+    for (int i = 0; i < mels; i++) {
+        const bool lerp = fwd_lo[i] + 1 == fwd_hi[i];
+        if (fwd_lo[i] < 0 || (lerp && fwd_hi[i] > B - 1) || (!lerp && fwd_hi[i] > B))
+            return fail(ctx, GOMEL_E_ARG, "forward mel table indexes outside the spectrum (the Go reference panics)");
+    }
+    for (int i = 0; i < B; i++) {
+        const bool copy = inv_lo[i] == inv_hi[i], lerp = inv_lo[i] + 1 == inv_hi[i] && inv_hi[i] < mels;
+        if (inv_lo[i] < 0 || (copy && inv_lo[i] >= mels) || (!copy && !lerp && inv_hi[i] > mels))
+            return fail(ctx, GOMEL_E_ARG, "inverse mel table indexes outside the mel axis (the Go reference panics)");
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
+    cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
+    ctx->d_fwd_lo = ctx->d_fwd_hi = ctx->d_inv_lo = ctx->d_inv_hi = nullptr; ctx->d_fwd_mod = nullptr; ctx->d_inv_mod = nullptr;
+    ctx->tbl_mels = 0;
+    std::vector<float> fm(mels);
+    for (int i = 0; i < mels; i++) fm[i] = (float)fwd_mod[i];
+    CU(cudaMalloc(&ctx->d_fwd_lo, mels * 4)); CU(cudaMalloc(&ctx->d_fwd_hi, mels * 4)); CU(cudaMalloc(&ctx->d_fwd_mod, mels * 4));
+    CU(cudaMalloc(&ctx->d_inv_lo, B * 4)); CU(cudaMalloc(&ctx->d_inv_hi, B * 4)); CU(cudaMalloc(&ctx->d_inv_mod, B * 8));
+    CU(cudaMemcpy(ctx->d_fwd_lo, fwd_lo, mels * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_fwd_hi, fwd_hi, mels * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_fwd_mod, fm.data(), mels * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_inv_lo, inv_lo, B * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_inv_hi, inv_hi, B * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_inv_mod, inv_mod, B * 8, cudaMemcpyHostToDevice));
+    ctx->tbl_mels = mels;
+    return 0;
+}
+
+// ------------------------------------------------------------------- host-buffer API
+static int host_forward(gomel_ctx* ctx, const gomel_config* cfg, int mode, const double* wav, long n, double* out)
+{
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!wav || !out || n <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    long np, fr, ola;
+    if (gomel_frames(cfg, n, &np, &fr, &ola)) return fail(ctx, GOMEL_E_ARG, "bad length");
+    const long per_frame = (mode == MODE_MEL) ? 2L * cfg->n_mels : 2L * cfg->n_freqs;
+    if (per_frame <= 0) return fail(ctx, GOMEL_E_ARG, "NumMels / NumFreqs must be positive");
+    void *d64, *dsig, *dout, *dout64;
+    if (int rc = ensure(ctx, S_F64IN, (size_t)n * 8, &d64)) return rc;
+    if (int rc = ensure(ctx, S_F32A, (size_t)np * 4, &dsig)) return rc;
+    if (int rc = ensure(ctx, S_F32B, (size_t)fr * per_frame * 4, &dout)) return rc;
+    if (int rc = ensure(ctx, S_F64OUT, (size_t)fr * per_frame * 8, &dout64)) return rc;
+    CU(cudaMemcpyAsync(d64, wav, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->st));
+    k_f64_to_f32_pad<<<grid_1d(np, 256), 256, 0, ctx->st>>>((const double*)d64, n, (float*)dsig, np);
+    ctx->launches++;
+    if (int rc = fwd_dev(ctx, cfg, mode, (const float*)dsig, 1, np, np, fr, (float*)dout)) return rc;
+    k_f32_to_f64<<<grid_1d(fr * per_frame, 256), 256, 0, ctx->st>>>((const float*)dout, (double*)dout64, fr * per_frame, 1.0);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, dout64, (size_t)fr * per_frame * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int gomel_to_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* wav, long n, double* mel_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return host_forward(ctx, cfg, MODE_MEL, wav, n, mel_out);
+}
+
+int gomel_to_phase(gomel_ctx* ctx, const gomel_config* cfg, const double* wav, long n, double* out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return host_forward(ctx, cfg, MODE_PHASE, wav, n, out);
+}
+
+int gomel_from_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* mel, long n_frames,
+                   const double* init_signal, unsigned long long seed, double* wav_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!mel || !wav_out || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    const long ola = kN + (n_frames - 1) * (long)kHop;
+    const long n_mel = n_frames * 2L * cfg->n_mels;
+    void *dmel, *dinit64 = nullptr, *dinit = nullptr, *dout, *dout64;
+    if (int rc = ensure(ctx, S_F64IN, (size_t)n_mel * 8, &dmel)) return rc;
+    if (int rc = ensure(ctx, S_F32B, (size_t)ola * 4, &dout)) return rc;
+    if (int rc = ensure(ctx, S_F64OUT, (size_t)ola * 8, &dout64)) return rc;
+    CU(cudaMemcpyAsync(dmel, mel, (size_t)n_mel * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (init_signal) {
+        if (int rc = ensure(ctx, S_F64IN2, (size_t)ola * 8, &dinit64)) return rc;
+        if (int rc = ensure(ctx, S_F32A, (size_t)ola * 4, &dinit)) return rc;
+        CU(cudaMemcpyAsync(dinit64, init_signal, (size_t)ola * 8, cudaMemcpyHostToDevice, ctx->st));
+        k_f64_to_f32_pad<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const double*)dinit64, ola, (float*)dinit, ola);
+        ctx->launches++;
+    }
+    if (int rc = from_mel_dev_impl<double>(ctx, cfg, (const double*)dmel, 1, n_frames, (const float*)dinit, seed, ola, (float*)dout))
+        return rc;
+    k_f32_to_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const float*)dout, (double*)dout64, ola, 1.0);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(wav_out, dout64, (size_t)ola * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int gomel_from_phase(gomel_ctx* ctx, const gomel_config* cfg, const double* spec, long n_frames, double* wav_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!spec || !wav_out || n_frames <= 0 || cfg->n_freqs <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    const long ola = kN + (n_frames - 1) * (long)kHop;
+    const long n_spec = n_frames * 2L * cfg->n_freqs;
+    void *d64, *d32, *dout, *dout64;
+    if (int rc = ensure(ctx, S_F64IN, (size_t)n_spec * 8, &d64)) return rc;
+    if (int rc = ensure(ctx, S_F32A, (size_t)n_spec * 4, &d32)) return rc;
+    if (int rc = ensure(ctx, S_F32B, (size_t)ola * 4, &dout)) return rc;
+    if (int rc = ensure(ctx, S_F64OUT, (size_t)ola * 8, &dout64)) return rc;
+    CU(cudaMemcpyAsync(d64, spec, (size_t)n_spec * 8, cudaMemcpyHostToDevice, ctx->st));
+    k_f64_to_f32_pad<<<grid_1d(n_spec, 256), 256, 0, ctx->st>>>((const double*)d64, n_spec, (float*)d32, n_spec);
+    ctx->launches++;
+    if (int rc = from_phase_dev_impl(ctx, cfg, (const float*)d32, 1, n_frames, ola, (float*)dout)) return rc;
+    k_f32_to_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const float*)dout, (double*)dout64, ola, 1.0);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(wav_out, dout64, (size_t)ola * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int gomel_image(gomel_ctx* ctx, const double* buf, long n_entries, int mels, unsigned short* out, double* minmax_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (!buf || !out || n_entries <= 0 || mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    // dumpbuffer covers stride*mels entries, stride = len/mels (mel/impl.go:17)
+    const long used = (n_entries / mels) * mels;
+    if (used <= 0) return fail(ctx, GOMEL_E_ARG, "fewer entries than one column");
+    void *d64, *dpart, *dout;
+    const int blocks = grid_1d(used, 256);
+    if (int rc = ensure(ctx, S_F64IN, (size_t)used * 16, &d64)) return rc;
+    if (int rc = ensure(ctx, S_MISC, (size_t)(blocks + 1) * 4 * 8, &dpart)) return rc;
+    if (int rc = ensure(ctx, S_F32B, (size_t)used * 2, &dout)) return rc;
+    double* dmm = (double*)dpart + (size_t)blocks * 4;
+    CU(cudaMemcpyAsync(d64, buf, (size_t)used * 16, cudaMemcpyHostToDevice, ctx->st));
+    k_minmax_f64<<<blocks, 256, 0, ctx->st>>>((const double*)d64, used, -99999999., 9999999., (double*)dpart);
+    k_minmax_final<<<1, 32, 0, ctx->st>>>((const double*)dpart, blocks, -99999999., 9999999., dmm);
+    k_quantise_u16<<<blocks, 256, 0, ctx->st>>>((const double*)d64, used, dmm, (unsigned short*)dout);
+    ctx->launches += 3;
+    CU(cudaMemcpyAsync(out, dout, (size_t)used * 2, cudaMemcpyDeviceToHost, ctx->st));
+    if (minmax_out) CU(cudaMemcpyAsync(minmax_out, dmm, 32, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int gomel_quantise(gomel_ctx* ctx, const double* buf, long n_entries, int mels, int flags, int ihs_passes,
+                   unsigned short* rgb_out, double* minmax_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (!buf || !rgb_out || n_entries <= 0 || mels <= 0 || ihs_passes < 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    const long used = (n_entries / mels) * mels;
+    if (used <= 0) return fail(ctx, GOMEL_E_ARG, "fewer entries than one column");
+    void *d64, *dpart, *dout;
+    const int blocks = grid_1d(used, 256);
+    if (int rc = ensure(ctx, S_F64IN, (size_t)used * 16, &d64)) return rc;
+    if (int rc = ensure(ctx, S_MISC, (size_t)(blocks + 1) * 4 * 8, &dpart)) return rc;
+    if (int rc = ensure(ctx, S_F32B, (size_t)used * 6, &dout)) return rc;
+    double* dmm = (double*)dpart + (size_t)blocks * 4;
+    const double big = 1.79769313486231570814527423731704357e+308;      // math.MaxFloat64
+    CU(cudaMemcpyAsync(d64, buf, (size_t)used * 16, cudaMemcpyHostToDevice, ctx->st));
+    if (ihs_passes > 0) { k_asinh_passes<<<blocks, 256, 0, ctx->st>>>((double*)d64, used * 2, ihs_passes, 0); ctx->launches++; }
+    k_minmax_f64<<<blocks, 256, 0, ctx->st>>>((const double*)d64, used, -big, big, (double*)dpart);
+    k_minmax_final<<<1, 32, 0, ctx->st>>>((const double*)dpart, blocks, -big, big, dmm);
+    ctx->launches += 2;
+    double mm[4];
+    CU(cudaMemcpyAsync(mm, dmm, 32, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (flags & GOMEL_Q_SINGLE_MINMAX) {
+        const double mx = mm[0] > mm[1] ? mm[0] : mm[1], mn = mm[2] < mm[3] ? mm[2] : mm[3];
+        mm[0] = mm[1] = mx; mm[2] = mm[3] = mn;
+        CU(cudaMemcpyAsync(dmm, mm, 32, cudaMemcpyHostToDevice, ctx->st));
+    }
+    k_quantise_rgb<<<blocks, 256, 0, ctx->st>>>((const double*)d64, used, dmm, (flags & GOMEL_Q_HDR) ? 65535 : 255,
+                                               (flags & GOMEL_Q_BLUE_WRAP) ? 1 : 0, (unsigned short*)dout);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(rgb_out, dout, (size_t)used * 6, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (minmax_out) memcpy(minmax_out, mm, 32);
+    return 0;
+}
+
+int gomel_dequantise(gomel_ctx* ctx, const unsigned short* rg, long n_entries, int hdr, double max0, double max1,
+                     double min0, double min1, int ihs_passes, double* out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (!rg || !out || n_entries <= 0 || ihs_passes < 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    void *din, *dout;
+    if (int rc = ensure(ctx, S_F32A, (size_t)n_entries * 4, &din)) return rc;
+    if (int rc = ensure(ctx, S_F64OUT, (size_t)n_entries * 16, &dout)) return rc;
+    CU(cudaMemcpyAsync(din, rg, (size_t)n_entries * 4, cudaMemcpyHostToDevice, ctx->st));
+    k_dequantise<<<grid_1d(n_entries, 256), 256, 0, ctx->st>>>((const unsigned short*)din, n_entries, hdr ? 65535.0 : 255.0,
+                                                              max0, max1, min0, min1, ihs_passes, (double*)dout);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, dout, (size_t)n_entries * 16, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------- device-resident API
+int gomel_dev_malloc(gomel_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaMalloc(out, bytes ? bytes : 16));
+    return 0;
+}
+int gomel_dev_free(gomel_ctx* ctx, void* p)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaFree(p));
+    return 0;
+}
+int gomel_host_malloc(gomel_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaMallocHost(out, bytes ? bytes : 16));
+    return 0;
+}
+int gomel_host_free(gomel_ctx* ctx, void* p)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaFreeHost(p));
+    return 0;
+}
+int gomel_copy_h2d(gomel_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->st));
+    return 0;
+}
+int gomel_copy_d2h(gomel_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    return 0;
+}
+int gomel_sync(gomel_ctx* ctx)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaStreamSynchronize(ctx->st_h2d));
+    CU(cudaStreamSynchronize(ctx->st_d2h));
+    return 0;
+}
+int gomel_timer_start(gomel_ctx* ctx)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaEventRecord(ctx->ev0, ctx->st));
+    return 0;
+}
+int gomel_timer_stop(gomel_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaEventRecord(ctx->ev1, ctx->st));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return 0;
+}
+
+int gomel_last_hot_kernel_ms(gomel_ctx* ctx, float* ms, int* launches)
+{
+    if (!ctx || !ms || !launches) return GOMEL_E_ARG;
+    Guard g(ctx);
+    *ms = 0.f; *launches = 0;
+    if (ctx->hot_launches <= 0) return fail(ctx, GOMEL_E_STATE, "no transform has run on this context yet");
+    CU(cudaEventSynchronize(ctx->ev_k1));
+    CU(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    *launches = ctx->hot_launches;
+    return 0;
+}
+
+int gomel_to_mel_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_sig, int n_clips, long sig_stride,
+                     long sig_len, long n_frames, float* d_mel)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return fwd_dev(ctx, cfg, MODE_MEL, d_sig, n_clips, sig_stride, sig_len, n_frames, d_mel);
+}
+int gomel_to_phase_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_sig, int n_clips, long sig_stride,
+                       long sig_len, long n_frames, float* d_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return fwd_dev(ctx, cfg, MODE_PHASE, d_sig, n_clips, sig_stride, sig_len, n_frames, d_out);
+}
+int gomel_stft_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_sig, int n_clips, long sig_stride,
+                   long sig_len, long n_frames, float* d_spec)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return fwd_dev(ctx, cfg, MODE_SPEC, d_sig, n_clips, sig_stride, sig_len, n_frames, d_spec);
+}
+int gomel_from_mel_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mel, int n_clips, long n_frames,
+                       const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return from_mel_dev_impl<float>(ctx, cfg, d_mel, n_clips, n_frames, d_init, seed, sig_stride, d_out);
+}
+int gomel_from_phase_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_spec, int n_clips, long n_frames,
+                         long sig_stride, float* d_out)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return from_phase_dev_impl(ctx, cfg, d_spec, n_clips, n_frames, sig_stride, d_out);
+}
+
+// ------------------------------------------------------------------- pipelined host batches
+// chunk c uses buffer set c&1; H2D on st_h2d, kernels on st, D2H on st_d2h, ordered by events
+int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
+                              const float* init, unsigned long long seed, float* out, int clips_per_chunk)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!mel || !out || n_clips <= 0 || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    const long ola = kN + (n_frames - 1) * (long)kHop;
+    const long mel_per = n_frames * 2L * cfg->n_mels;
+    int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
+    if (cpc > n_clips) cpc = n_clips;
+    void *dmel[2], *dinit[2] = { nullptr, nullptr }, *dout[2];
+    for (int b = 0; b < 2; b++) {
+        if (int rc = ensure(ctx, S_CH0 + b, (size_t)cpc * mel_per * 4, &dmel[b])) return rc;
+        if (int rc = ensure(ctx, S_CH2 + b, (size_t)cpc * ola * 4, &dout[b])) return rc;
+        if (init) { if (int rc = ensure(ctx, S_CH4 + b, (size_t)cpc * ola * 4, &dinit[b])) return rc; }
+    }
+    cudaEvent_t up[2], done[2], down[2];
+    for (int b = 0; b < 2; b++) {
+        CU(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
+    }
+    int rc = 0;
+    const int n_chunks = (n_clips + cpc - 1) / cpc;
+    for (int c = 0; c < n_chunks && !rc; c++) {
+        const int b = c & 1, c0 = c * cpc, nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+        if (c >= 2) cudaStreamWaitEvent(ctx->st_h2d, done[b], 0);        // inputs of chunk c-2 consumed
+        cudaMemcpyAsync(dmel[b], mel + (size_t)c0 * mel_per, (size_t)nc * mel_per * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
+        if (init) cudaMemcpyAsync(dinit[b], init + (size_t)c0 * ola, (size_t)nc * ola * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
+        cudaEventRecord(up[b], ctx->st_h2d);
+        cudaStreamWaitEvent(ctx->st, up[b], 0);
+        if (c >= 2) cudaStreamWaitEvent(ctx->st, down[b], 0);            // output buffer of chunk c-2 drained
+        rc = from_mel_dev_impl<float>(ctx, cfg, (const float*)dmel[b], nc, n_frames, (const float*)dinit[b],
+                                      seed + (unsigned long long)c0, ola, (float*)dout[b]);
+        cudaEventRecord(done[b], ctx->st);
+        cudaStreamWaitEvent(ctx->st_d2h, done[b], 0);
+        cudaMemcpyAsync(out + (size_t)c0 * ola, dout[b], (size_t)nc * ola * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
+        cudaEventRecord(down[b], ctx->st_d2h);
+    }
+    cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_d2h);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); }
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int gomel_to_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float* wav, int n_clips, long n_samples,
+                            float* mel_out, int clips_per_chunk)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (!wav || !mel_out || n_clips <= 0 || n_samples <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    long np, fr, ola;
+    if (gomel_frames(cfg, n_samples, &np, &fr, &ola)) return fail(ctx, GOMEL_E_ARG, "bad length");
+    const long stride = (np + 3) & ~3L;
+    const long mel_per = fr * 2L * cfg->n_mels;
+    int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
+    if (cpc > n_clips) cpc = n_clips;
+    void *dsig[2], *dout[2];
+    for (int b = 0; b < 2; b++) {
+        if (int rc = ensure(ctx, S_CH0 + b, (size_t)cpc * stride * 4, &dsig[b])) return rc;
+        if (int rc = ensure(ctx, S_CH2 + b, (size_t)cpc * mel_per * 4, &dout[b])) return rc;
+        CU(cudaMemsetAsync(dsig[b], 0, (size_t)cpc * stride * 4, ctx->st_h2d));   // pad() zeros, written once
+    }
+    cudaEvent_t up[2], done[2], down[2];
+    for (int b = 0; b < 2; b++) {
+        CU(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
+    }
+    int rc = 0;
+    const int n_chunks = (n_clips + cpc - 1) / cpc;
+    for (int c = 0; c < n_chunks && !rc; c++) {
+        const int b = c & 1, c0 = c * cpc, nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+        if (c >= 2) cudaStreamWaitEvent(ctx->st_h2d, done[b], 0);
+        cudaMemcpy2DAsync(dsig[b], (size_t)stride * 4, wav + (size_t)c0 * n_samples, (size_t)n_samples * 4,
+                          (size_t)n_samples * 4, nc, cudaMemcpyHostToDevice, ctx->st_h2d);
+        cudaEventRecord(up[b], ctx->st_h2d);
+        cudaStreamWaitEvent(ctx->st, up[b], 0);
+        if (c >= 2) cudaStreamWaitEvent(ctx->st, down[b], 0);
+        rc = fwd_dev(ctx, cfg, MODE_MEL, (const float*)dsig[b], nc, stride, np, fr, (float*)dout[b]);
+        cudaEventRecord(done[b], ctx->st);
+        cudaStreamWaitEvent(ctx->st_d2h, done[b], 0);
+        cudaMemcpyAsync(mel_out + (size_t)c0 * mel_per, dout[b], (size_t)nc * mel_per * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
+        cudaEventRecord(down[b], ctx->st_d2h);
+    }
+    cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_d2h);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); }
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

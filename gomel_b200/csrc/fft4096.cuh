@@ -1,0 +1,227 @@
+// fft4096.cuh -- complex FFT-4096 for one CTA of 256 threads, sm_100a.
+//
+// Replaces, for the gomel hot path, the per-frame calls into go-dsp's radix-2 FFT
+// (fft.FFTReal at mel/mel.go:95, fft.IFFT at mel/mel.go:116 and phase/phase.go:103, and the FFT
+// inside gossp STFT.STFT at mel/mel.go:52, phase/phase.go:47).
+//
+// Design (see DESIGN.md "FFT core"):
+//  * TWO real frames ride one complex transform: z = w*(xA + i*xB).  4096 = 16*16*16, so a
+//    transform is three radix-16 register butterflies per thread with two shared-memory
+//    exchanges between them.  Thread t holds points n = t + 256*m, m = 0..15.
+//  * forward = decimation in frequency (natural in, digit-reversed out), inverse = decimation in
+//    time (digit-reversed in, natural out): the spectrum never has to be re-ordered, the
+//    point-wise stage between them works on the digit-reversed layout
+//        thread (k0,k1), slot k2  <->  bin k = k0 + 16*k1 + 256*k2.
+//  * the exchange buffer is used IN PLACE: every thread always writes exactly the logical cells
+//    it read last, so one __syncthreads per exchange (RAW only) is enough.  Physical address of
+//    logical cell L is L + (L>>4) (one pad per 16), which makes all three access patterns
+//    bank-conflict free with compile-time slot offsets.
+//  * bins k and 4096-k (needed together to split the two real spectra) are mapped to lanes of
+//    the same warp, so that split is done with warp shuffles, not another smem pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gomel {
+
+constexpr int kN = 4096;          // Resolut
+constexpr int kThreads = 256;     // threads per CTA = points / 16
+constexpr int kXchgCells = 16 * 272;                       // padded float2 cells
+constexpr int kXchgBytes = kXchgCells * 8;                 // 34,816 B
+constexpr int kT1Cells = 15 * 256;                         // W4096^(t*k0), k0 = 1..15
+constexpr int kT2Cells = 16 * 16;                          // W256^(n0*k1)
+constexpr int kWinCells = 4096;                            // window, [m][t]
+constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 49,152 B
+constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 83,968 B
+
+struct Smem {
+    float2* T1;     // [15][256]
+    float2* T2;     // [16][16]
+    float*  win;    // [16][256]
+    float2* xb;     // exchange buffer, kXchgCells
+};
+
+__device__ __forceinline__ Smem carve_smem(unsigned char* base)
+{
+    Smem s;
+    s.T1 = reinterpret_cast<float2*>(base);
+    s.T2 = s.T1 + kT1Cells;
+    s.win = reinterpret_cast<float*>(s.T2 + kT2Cells);
+    s.xb = reinterpret_cast<float2*>(s.win + kWinCells);
+    return s;
+}
+
+// global table blob layout == smem table layout (T1 | T2 | win), kTableBytes long
+__device__ __forceinline__ void load_tables(const Smem& s, const float4* __restrict__ g, int t)
+{
+    float4* d = reinterpret_cast<float4*>(s.T1);
+#pragma unroll 4
+    for (int i = t; i < kTableBytes / 16; i += kThreads) d[i] = __ldg(g + i);
+}
+
+// per-thread indices for the three exchange patterns and the spectrum layout
+struct Lanes {
+    int t;         // thread id; pattern (a): cell k0*272 + base_a
+    int base_a;    // t + (t>>4)
+    int base_b;    // pattern (b): thread (k0=t>>4, n0=t&15), slot r: base_b + r*17
+    int base_c;    // pattern (c): thread (k0c,k1c), slot n0: base_c + n0
+    int k0c, k1c;  // spectrum digits owned after the forward transform
+    int klow;      // k0c + 16*k1c : bins k = klow + 256*k2
+    int src;       // lane holding bins 4096-k (partner)
+    bool special;  // klow == 0: partner of slot k2 is own slot (16-k2)&15
+};
+
+__device__ __forceinline__ Lanes make_lanes()
+{
+    Lanes L;
+    const int t = threadIdx.x, w = t >> 5, l = t & 31;
+    L.t = t;
+    L.base_a = t + (t >> 4);
+    L.base_b = (t >> 4) * 272 + (t & 15);
+    if (l < 16) { L.k0c = w; L.k1c = l; }
+    else        { L.k0c = (w == 0) ? 8 : 16 - w; L.k1c = 31 - l; }
+    L.base_c = L.k0c * 272 + L.k1c * 17;
+    L.klow = L.k0c + 16 * L.k1c;
+    if (w == 0) L.src = (l < 16) ? ((16 - l) & 15) : (47 - l);
+    else        L.src = l ^ 16;
+    L.special = (t == 0);
+    return L;
+}
+
+// ---------------------------------------------------------------- complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// a * (wr + i*wi)
+__device__ __forceinline__ float2 cmul(float2 a, float wr, float wi)
+{
+    return make_float2(fmaf(-a.y, wi, a.x * wr), fmaf(a.y, wr, a.x * wi));
+}
+template <bool INV>
+__device__ __forceinline__ float2 cmul_tw(float2 a, float2 w)   // forward: a*w ; inverse: a*conj(w)
+{
+    return INV ? cmul(a, w.x, -w.y) : cmul(a, w.x, w.y);
+}
+
+// 4-point DFT, forward kernel e^{-2 pi i/4} (INV: conjugate)
+template <bool INV>
+__device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3)
+{
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    if (!INV) { a1 = make_float2(t1.x + t3.y, t1.y - t3.x); a3 = make_float2(t1.x - t3.y, t1.y + t3.x); }
+    else      { a1 = make_float2(t1.x - t3.y, t1.y + t3.x); a3 = make_float2(t1.x + t3.y, t1.y - t3.x); }
+}
+
+// multiply by W16^e (forward) or its conjugate (INV); e in {1,2,3,4,6,9}
+template <bool INV, int E>
+__device__ __forceinline__ float2 mul_w16(float2 a)
+{
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    if (E == 0) return a;
+    if (E == 1) return INV ? cmul(a, c1, s1) : cmul(a, c1, -s1);
+    if (E == 2) return INV ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
+    if (E == 3) return INV ? cmul(a, s1, c1) : cmul(a, s1, -c1);
+    if (E == 4) return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    if (E == 6) return INV ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+    /* E == 9 */ return INV ? cmul(a, -c1, -s1) : cmul(a, -c1, s1);
+}
+
+// 16-point DFT in registers, natural order in and out:  v[k] <- sum_m v[m] W16^{mk}
+template <bool INV>
+__device__ __forceinline__ void radix16(float2 (&v)[16])
+{
+    // step 1: over m1 for each m0 (elements m0, m0+4, m0+8, m0+12) -> B[m0][ka] at v[m0+4ka]
+#pragma unroll
+    for (int m0 = 0; m0 < 4; m0++) radix4<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]);
+    // step 2: inner twiddles W16^{m0*ka}
+    v[5]  = mul_w16<INV, 1>(v[5]);   v[9]  = mul_w16<INV, 2>(v[9]);   v[13] = mul_w16<INV, 3>(v[13]);
+    v[6]  = mul_w16<INV, 2>(v[6]);   v[10] = mul_w16<INV, 4>(v[10]);  v[14] = mul_w16<INV, 6>(v[14]);
+    v[7]  = mul_w16<INV, 3>(v[7]);   v[11] = mul_w16<INV, 6>(v[11]);  v[15] = mul_w16<INV, 9>(v[15]);
+    // step 3: over m0 for each ka (elements 4ka .. 4ka+3) -> X[ka + 4kb]
+    float2 o[16];
+#pragma unroll
+    for (int ka = 0; ka < 4; ka++) {
+        float2 b0 = v[4 * ka], b1 = v[4 * ka + 1], b2 = v[4 * ka + 2], b3 = v[4 * ka + 3];
+        radix4<INV>(b0, b1, b2, b3);
+        o[ka] = b0; o[ka + 4] = b1; o[ka + 8] = b2; o[ka + 12] = b3;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = o[i];
+}
+
+// ---------------------------------------------------------------- forward transform (DIF)
+// in : v[m]  = z[t + 256*m]
+// out: v[k2] = Z[klow + 256*k2]        (un-normalised, kernel e^{-2 pi i nk/N})
+__device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, const Lanes& L)
+{
+    radix16<false>(v);                                               // n2 -> k0
+#pragma unroll
+    for (int k0 = 1; k0 < 16; k0++) v[k0] = cmul_tw<false>(v[k0], s.T1[(k0 - 1) * 256 + L.t]);
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0++) s.xb[k0 * 272 + L.base_a] = v[k0];      // pattern (a)
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * 17];             // pattern (b)
+    radix16<false>(v);                                               // n1 -> k1
+#pragma unroll
+    for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul_tw<false>(v[k1], s.T2[k1 * 16 + (L.t & 15)]);
+#pragma unroll
+    for (int r = 0; r < 16; r++) s.xb[L.base_b + r * 17] = v[r];             // pattern (b), in place
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; c++) v[c] = s.xb[L.base_c + c];                  // pattern (c)
+    radix16<false>(v);                                               // n0 -> k2
+}
+
+// ---------------------------------------------------------------- inverse transform (DIT)
+// in : v[k2] = Z[klow + 256*k2]
+// out: v[m]  = sum_k Z[k] e^{+2 pi i nk/N},  n = t + 256*m   (caller folds in 1/N)
+__device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, const Lanes& L)
+{
+    radix16<true>(v);                                                // k2 -> n0
+#pragma unroll
+    for (int n0 = 1; n0 < 16; n0++) v[n0] = cmul_tw<true>(v[n0], s.T2[n0 * 16 + L.k1c]);
+#pragma unroll
+    for (int c = 0; c < 16; c++) s.xb[L.base_c + c] = v[c];                  // pattern (c), in place
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * 17];             // pattern (b)
+    radix16<true>(v);                                                // k1 -> n1
+#pragma unroll
+    for (int r = 0; r < 16; r++) s.xb[L.base_b + r * 17] = v[r];             // pattern (b), in place
+    __syncthreads();
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0++) v[k0] = s.xb[k0 * 272 + L.base_a];       // pattern (a)
+#pragma unroll
+    for (int k0 = 1; k0 < 16; k0++) v[k0] = cmul_tw<true>(v[k0], s.T1[(k0 - 1) * 256 + L.t]);
+    radix16<true>(v);                                                // k0 -> n2
+}
+
+// ---------------------------------------------------------------- partner fetch
+// P[k2] = Z[4096 - k] for the bins this thread holds (k = klow + 256*k2); processes the two
+// slots j and 15-j together.  Generic lanes: partner lane L.src, partner slot 15-k2.
+// The single special thread (klow == 0) pairs with its own slot (16-k2)&15.
+template <bool WARP0>
+__device__ __forceinline__ void fetch_partner(const float2 (&v)[16], int j, const Lanes& L,
+                                              float2& p_lo, float2& p_hi, float2& saved)
+{
+    // p_lo = partner of slot j, p_hi = partner of slot 15-j
+    float2 a, b;
+    a.x = __shfl_sync(0xffffffffu, v[15 - j].x, L.src);
+    a.y = __shfl_sync(0xffffffffu, v[15 - j].y, L.src);
+    b.x = __shfl_sync(0xffffffffu, v[j].x, L.src);
+    b.y = __shfl_sync(0xffffffffu, v[j].y, L.src);
+    if (WARP0) {
+        if (L.special) {
+            // slot j pairs with original slot 16-j (updated one step ago -> `saved`), j=0 with itself;
+            // slot 15-j pairs with slot j+1 (still original)
+            a = (j == 0) ? v[0] : saved;
+            b = v[j + 1 > 15 ? 15 : j + 1];
+        }
+        saved = v[15 - j];      // original value of slot 15-j, needed next step as slot 16-(j+1)
+    }
+    p_lo = a; p_hi = b;
+}
+
+}  // namespace gomel

@@ -1,0 +1,642 @@
+// kernels.cuh -- sm_100a kernels of the gomel spectrogram hot path.
+//
+// All transforms process frames in PAIRS (frame A = 2p, frame B = 2p+1 ride the real and
+// imaginary lane of one complex FFT-4096, fft4096.cuh).  A CTA walks a TILE of consecutive
+// frames of one clip.  Because the hop (Window, 1280) is a multiple of the per-thread sample
+// stride (256), the samples a thread needs for the next pair are the ones it already holds,
+// shifted by 2*hop/256 slots: the analysis input window and the overlap-add accumulator both
+// live in registers and slide; per pair a thread reads 2*hop/256 new samples and writes
+// 2*hop/256 finished ones -- exactly the algorithmic bytes of SURVEY.md 8(d).
+#pragma once
+#include "fft4096.cuh"
+
+namespace gomel {
+
+constexpr int kMagStride = 2052;     // floats per magnitude row: 2049 bins, 16-byte aligned rows
+
+// position of bin k inside a magnitude row: low byte nibble-swapped so that the digit-reversed
+// spectrum layout of fft4096_fwd reads rows with unit stride across a half-warp
+__host__ __device__ __forceinline__ int mag_pos(int k)
+{
+    return (k >= 2048) ? 2048 : ((k & ~255) | ((k & 15) << 4) | ((k >> 4) & 15));
+}
+
+// ------------------------------------------------------------------ small conversion kernels
+__global__ void k_f64_to_f32_pad(const double* __restrict__ in, long n_in, float* __restrict__ out, long n_out)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n_out; i += step) out[i] = (i < n_in) ? (float)in[i] : 0.0f;
+}
+__global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, long n, double scale)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) out[i] = (double)in[i] * scale;
+}
+__global__ void k_fill_f32(float* __restrict__ out, long n, float v)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) out[i] = v;
+}
+// counter-based U[0,1) fill for the Griffin-Lim start signal when the caller injects none
+// (mel/mel.go:80-83 draws rand.Float64(); same distribution, not bit-compatible with math/rand)
+__global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long long seed)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        out[i] = (float)(z >> 40) * (1.0f / 16777216.0f);
+    }
+}
+
+// ------------------------------------------------------------------ tile geometry
+struct Tiling {
+    int n_frames;        // frames per clip
+    int tile_frames;     // T, even
+    int n_tiles;         // ceil(n_frames / T)
+    long sig_stride;     // floats between clips in signal buffers
+    long sig_len;        // valid samples per clip (loads beyond read as 0, stores beyond dropped)
+};
+
+// ------------------------------------------------------------------ K1+K2 / K1+K4: STFT forward
+// Replaces gossp STFT.STFT + the magnitude loop + domel + spectral_normalize of mel.ToMel
+// (mel/mel.go:50-70, mel/impl.go:310-345, :410-419)  [MODE_MEL]
+// and gossp STFT.STFT + the (Im,Re) gather + shrink of phase.ToPhase
+// (phase/phase.go:45-66, phase/impl.go:383-391)      [MODE_PHASE]
+enum { MODE_MEL = 0, MODE_PHASE = 1, MODE_SPEC = 2 };
+
+struct FwdParams {
+    const float* sig;        // [clips][sig_stride], zero padded per pad()
+    const float4* tables;
+    Tiling tl;
+    // MODE_MEL
+    const int* fwd_lo; const int* fwd_hi; const float* fwd_mod; int n_mels;
+    float* mel_out;          // [clips][frames][n_mels][2]  ln(max(v,1e-5))
+    // MODE_PHASE
+    int n_freqs;
+    float2* phase_out;       // [clips][frames][n_freqs] (Im X[j+1], Re X[j+1])
+    // MODE_SPEC (tests): half spectrum [clips][frames][2049] natural order
+    float2* spec_out;
+};
+
+template <int HS, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve_smem(smem_raw);
+    const Lanes L = make_lanes();
+    load_tables(s, p.tables, L.t);
+    constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS;
+    const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
+    const int f0 = tile * p.tl.tile_frames;
+    const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
+    const int npairs = (nf + 1) >> 1;
+    const float* __restrict__ sig = p.sig + (long)clip * p.tl.sig_stride + (long)f0 * H;
+    const long lim = p.tl.sig_len - (long)f0 * H;
+    const int t = L.t;
+
+    float raw[NR];
+#pragma unroll
+    for (int j = 0; j < KEEP; j++) { const long o = j * 256 + t; raw[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
+    __syncthreads();
+
+    for (int pr = 0; pr < npairs; pr++) {
+        const long off0 = (long)pr * 2 * H;
+#pragma unroll
+        for (int j = KEEP; j < NR; j++) { const long o = off0 + j * 256 + t; raw[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) { const float w = s.win[m * 256 + t]; v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
+#pragma unroll
+        for (int j = 0; j < KEEP; j++) raw[j] = raw[j + SH];
+
+        fft4096_fwd(v, s, L);
+
+        const int fA = f0 + 2 * pr;
+        const bool validB = (fA + 1) < p.tl.n_frames;
+
+        // split the two real spectra: XA[k] = (Z[k] + conj Z[N-k])/2, XB[k] = (Z[k] - conj Z[N-k])/(2i)
+        // only slots k2 < 8 (k < 2048) and the Nyquist bin carry new information
+        float2 xa[9], xb[9];
+        {
+            float2 saved = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float2 plo, phi;
+                if ((t >> 5) == 0) fetch_partner<true>(v, j, L, plo, phi, saved);
+                else               fetch_partner<false>(v, j, L, plo, phi, saved);
+                xa[j] = make_float2(0.5f * (v[j].x + plo.x), 0.5f * (v[j].y - plo.y));
+                xb[j] = make_float2(0.5f * (v[j].y + plo.y), 0.5f * (plo.x - v[j].x));
+                if (j == 7) {   // slot 8: k = klow + 2048, only k = 2048 (special thread) is a new bin
+                    xa[8] = make_float2(0.5f * (v[8].x + phi.x), 0.5f * (v[8].y - phi.y));
+                    xb[8] = make_float2(0.5f * (v[8].y + phi.y), 0.5f * (phi.x - v[8].x));
+                }
+            }
+        }
+
+        __syncthreads();     // every thread is done reading the exchange buffer (pattern c)
+        if (MODE == MODE_MEL) {
+            float* SA = reinterpret_cast<float*>(s.xb);
+            float* SB = SA + 2184;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = L.klow + 256 * j, q = k + (k >> 4);
+                SA[q] = sqrtf(xa[j].x * xa[j].x + xa[j].y * xa[j].y);
+                SB[q] = sqrtf(xb[j].x * xb[j].x + xb[j].y * xb[j].y);
+            }
+            if (L.special) {
+                SA[2048 + 128] = sqrtf(xa[8].x * xa[8].x + xa[8].y * xa[8].y);
+                SB[2048 + 128] = sqrtf(xb[8].x * xb[8].x + xb[8].y * xb[8].y);
+            }
+            __syncthreads();
+            // domel: out[(frame, mel, ch)], ch0 over |X[k]|, ch1 over |X[N-1-k]| = |X[k+1]|
+            const int per_frame = 2 * p.n_mels;
+            float* outp = p.mel_out + ((long)clip * p.tl.n_frames + fA) * per_frame;
+            for (int o = t; o < 2 * per_frame; o += kThreads) {
+                const int fr = o / per_frame, r = o - fr * per_frame, mel = r >> 1, ch = r & 1;
+                if (fr == 1 && !validB) continue;
+                const float* S = fr ? SB : SA;
+                const int lo = p.fwd_lo[mel], hi = p.fwd_hi[mel];
+                float total = 0.0f;
+                if (lo + 1 == hi) {
+                    const float md = p.fwd_mod[mel];
+                    const int a = lo + ch, b = hi + ch;
+                    total = S[a + (a >> 4)] * (1.0f - md);
+                    total += S[b + (b >> 4)] * md;
+                } else {
+                    for (int k = lo + ch; k < hi + ch; k++) total += S[k + (k >> 4)];
+                    total /= (float)(hi - lo + 1);
+                }
+                total = (total < 1e-5f) ? 1e-5f : total;
+                outp[o] = logf(total);
+            }
+        } else if (MODE == MODE_PHASE) {
+            float2* SA = s.xb;
+            float2* SB = s.xb + 2176;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = L.klow + 256 * j;          // bin k -> entry k-1
+                if (k >= 1) {
+                    const int e = k - 1, q = e + (e >> 4);
+                    SA[q] = make_float2(xa[j].y, xa[j].x);
+                    SB[q] = make_float2(xb[j].y, xb[j].x);
+                }
+            }
+            if (L.special) {
+                const int e = 2047, q = e + (e >> 4);
+                SA[q] = make_float2(xa[8].y, xa[8].x);
+                SB[q] = make_float2(xb[8].y, xb[8].x);
+            }
+            __syncthreads();
+            float2* outp = p.phase_out + ((long)clip * p.tl.n_frames + fA) * p.n_freqs;
+            const int nfq = p.n_freqs;
+            for (int o = t; o < 2 * nfq; o += kThreads) {
+                const int fr = (o >= nfq), e = o - fr * nfq;
+                if (fr == 1 && !validB) continue;
+                outp[o] = (fr ? SB : SA)[e + (e >> 4)];
+            }
+        } else {
+            float2* SA = s.xb;
+            float2* SB = s.xb + 2176;      // 2049 + 128 pad = 2177 cells > 2176: bin 2048 goes straight out
+            float2* outp = p.spec_out + ((long)clip * p.tl.n_frames + fA) * 2049;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = L.klow + 256 * j, q = k + (k >> 4);
+                SA[q] = xa[j]; SB[q] = xb[j];
+            }
+            if (L.special) { outp[2048] = xa[8]; if (validB) outp[2049 + 2048] = xb[8]; }
+            __syncthreads();
+            for (int o = t; o < 2 * 2048; o += kThreads) {
+                const int fr = (o >= 2048), e = o - fr * 2048;
+                if (fr == 1 && !validB) continue;
+                outp[fr * 2049 + e] = (fr ? SB : SA)[e + (e >> 4)];
+            }
+        }
+        __syncthreads();     // epilogue reads done before the next pair's pattern-(a) writes
+    }
+}
+
+// ------------------------------------------------------------------ K3: mel -> GL target magnitudes
+// Replaces spectral_denormalize + undomel + Mel.undospectrum (mel/impl.go:421-427, :347-384,
+// :386-408) reduced to the 2049 magnitudes mel.ISTFT actually uses: |X[k]| = ch0[k] for k < 2048
+// and ch1[2047] for k = 2048 (cmplx.Abs at mel/mel.go:99).  Output rows are pre-scaled by 1/N
+// (the IFFT normalisation) and stored in mag_pos() order.  Arithmetic in float64.
+template <typename T>
+__global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel, float* __restrict__ mags,
+                                                       const int* __restrict__ inv_lo, const int* __restrict__ inv_hi,
+                                                       const double* __restrict__ inv_mod, int n_mels,
+                                                       double tune_add, double tune_mul, long n_rows)
+{
+    extern __shared__ double e[];     // [n_mels][2]
+    for (long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const T* m = mel + row * 2 * n_mels;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n_mels; i += blockDim.x) e[i] = exp((double)m[i]);
+        __syncthreads();
+        float* out = mags + row * kMagStride;
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+            const int lo = inv_lo[i], hi = inv_hi[i];
+            const int nch = (i == 2047) ? 2 : 1;
+            for (int l = 0; l < nch; l++) {
+                double total = 0.0;
+                if (lo == hi) total = e[2 * lo + l];
+                else if (lo + 1 == hi && hi < n_mels) {
+                    const double md = inv_mod[i];
+                    total = e[2 * lo + l] * (1.0 - md);
+                    total += e[2 * hi + l] * md;
+                } else {
+                    for (int k = lo; k < hi; k++) total += e[2 * k + l];
+                    total /= (double)(hi - lo + 1);
+                }
+                const double v = fabs((total - tune_add) / tune_mul) * (1.0 / 4096.0);
+                out[l ? 2048 : mag_pos(i)] = (float)v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ shared pieces of the synthesis kernels
+constexpr int kMaxHalo = 15 * 256;
+
+struct SynParams {
+    const float4* tables;
+    Tiling tl;
+    const float* sig_in;     // GL: previous signal [clips][sig_stride]
+    float* sig_out;          // new signal
+    const float* hb_in;      // head partials of the previous iteration [clips][n_tiles][halo], or null
+    float* hb_out;           // head partials of this iteration
+    const float* mags;       // GL: [clips][frames][kMagStride]
+    // phase ISTFT
+    const float2* spec;      // [clips][frames][n_freqs] (Im, Re)
+    int n_freqs;
+    const float* gain_head; const float* gain_mid; const float* gain_tail;   // window-sum normalisation
+    int head_len, tail_len;
+};
+
+__device__ __forceinline__ float2 subst_phase(float2 X, float M)
+{
+    // cmplx.Rect(M, cmplx.Phase(X)) = M * X/|X|; Phase(0) = 0 -> (M, 0)   (mel/mel.go:98-102)
+    const float n = fmaf(X.x, X.x, X.y * X.y);
+    if (n > 1e-30f) { const float r = M * rsqrtf(n); return make_float2(X.x * r, X.y * r); }
+    return make_float2(M, 0.0f);
+}
+
+// ------------------------------------------------------------------ K5: one Griffin-Lim iteration
+// Replaces one pass of the loop body of mel.ISTFT (mel/mel.go:85-136): frame gather x Hann ->
+// FFTReal -> Rect(|S|, Phase(F)) -> conj symmetry -> IFFT -> x Hann -> overlap-add, NO window-sum
+// normalisation (commented out in the reference, mel/mel.go:113,122,127-132).  Jacobi update:
+// reads sig_in only, writes sig_out only.
+// Tile edges: samples whose contributing frames straddle two tiles are produced as two partial
+// sums -- the earlier tile's into sig_out (its tail), the later tile's into hb_out (its head) --
+// and summed on load (a+b is commutative, so both readers see the same value).
+template <int HS>
+__global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve_smem(smem_raw);
+    const Lanes L = make_lanes();
+    load_tables(s, p.tables, L.t);
+    constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
+    const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
+    const int f0 = tile * p.tl.tile_frames;
+    const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
+    const int npairs = (nf + 1) >> 1;
+    const int tile_len = p.tl.tile_frames * H;
+    const long sbase = (long)f0 * H;
+    const float* __restrict__ sin_ = p.sig_in + (long)clip * p.tl.sig_stride + sbase;
+    float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
+    const long lim = p.tl.sig_len - sbase;
+    const bool has_prev = tile > 0, has_next = (tile + 1) < p.tl.n_tiles;
+    const float* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)clip * p.tl.n_tiles + tile) * HALO : nullptr;
+    const float* __restrict__ hin_next = hin_own ? hin_own + HALO : nullptr;
+    float* __restrict__ hout = p.hb_out + ((long)clip * p.tl.n_tiles + tile) * HALO;
+    const int t = L.t;
+
+    auto ld = [&](int row) -> float {          // row: sample offset inside the tile, multiple of 256
+        const int o = row + t;
+        float x = (o < lim) ? __ldg(sin_ + o) : 0.0f;
+        if (hin_own) {
+            if (has_prev && row < HALO) x += __ldg(hin_own + o);
+            else if (has_next && row >= tile_len) x += __ldg(hin_next + (o - tile_len));
+        }
+        return x;
+    };
+    auto st = [&](int row, float val) {
+        const int o = row + t;
+        if (o >= lim) return;
+        if (has_prev && row < HALO) hout[o] = val;
+        else sout[o] = val;
+    };
+
+    float raw[NR], acc[NR];
+#pragma unroll
+    for (int j = 0; j < KEEP; j++) { raw[j] = ld(j * 256); acc[j] = 0.0f; }
+
+    const int idx_lo = ((L.klow & 15) << 4) | (L.klow >> 4);
+    const int x256 = 256 - L.klow;
+    const int idx_hi = L.klow ? (((x256 & 15) << 4) | (x256 >> 4)) : 256;
+    const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
+    __syncthreads();
+
+    for (int pr = 0; pr < npairs; pr++) {
+        const int off0 = pr * 2 * H;
+#pragma unroll
+        for (int j = KEEP; j < NR; j++) { raw[j] = ld(off0 + j * 256); acc[j] = 0.0f; }
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) { const float w = s.win[m * 256 + t]; v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
+#pragma unroll
+        for (int j = 0; j < KEEP; j++) raw[j] = raw[j + SH];
+
+        fft4096_fwd(v, s, L);
+
+        // magnitude substitution on both frames at once.  With P = Z[N-k]:
+        //   2*XA[k] = Z + conj P,  2*XB[k] = (Z - conj P)/i ; Y = M * X/|X| ; Z' = YA + i*YB
+        const bool validB = (f0 + 2 * pr + 1) < p.tl.n_frames;
+        const float* __restrict__ mA = mrow + (long)(2 * pr) * kMagStride;
+        const float* __restrict__ mB = mA + kMagStride;
+        {
+            float2 saved = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float mAlo = __ldg(mA + j * 256 + idx_lo), mAhi = __ldg(mA + j * 256 + idx_hi);
+                const float mBlo = validB ? __ldg(mB + j * 256 + idx_lo) : 0.0f;
+                const float mBhi = validB ? __ldg(mB + j * 256 + idx_hi) : 0.0f;
+                float2 plo, phi;
+                if ((t >> 5) == 0) fetch_partner<true>(v, j, L, plo, phi, saved);
+                else               fetch_partner<false>(v, j, L, plo, phi, saved);
+                {
+                    const float2 z = v[j];
+                    const float2 ya = subst_phase(make_float2(z.x + plo.x, z.y - plo.y), mAlo);
+                    const float2 yb = subst_phase(make_float2(z.y + plo.y, plo.x - z.x), mBlo);
+                    v[j] = make_float2(ya.x - yb.y, ya.y + yb.x);
+                }
+                {
+                    const float2 z = v[15 - j];
+                    const float2 ya = subst_phase(make_float2(z.x + phi.x, z.y - phi.y), mAhi);
+                    const float2 yb = subst_phase(make_float2(z.y + phi.y, phi.x - z.x), mBhi);
+                    v[15 - j] = make_float2(ya.x - yb.y, ya.y + yb.x);
+                }
+            }
+        }
+
+        fft4096_inv(v, s, L);
+
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const float w = s.win[m * 256 + t];
+            acc[m] = fmaf(v[m].x, w, acc[m]);
+            acc[m + HS] = fmaf(v[m].y, w, acc[m + HS]);
+        }
+#pragma unroll
+        for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
+#pragma unroll
+        for (int j = 0; j < KEEP; j++) acc[j] = acc[j + SH];
+    }
+#pragma unroll
+    for (int j = 0; j < KEEP; j++) st(npairs * 2 * H + j * 256, acc[j]);
+}
+
+// ------------------------------------------------------------------ K4+K6: phase ISTFT
+// Replaces grow + Phase.undospectrum + phase.ISTFT + the VolumeBoost loop of phase.FromPhase
+// (phase/impl.go:392-403, phase/phase.go:72-91, :93-133, :146-150).  The window-sum
+// normalisation is data independent: gain tables (1/ws, 1/thr or 1, times VolumeBoost) are built
+// on the host in float64.  Samples shared by two tiles are left un-normalised (partials in
+// sig_out / hb_out) and finished by k_halo_fix.
+__device__ __forceinline__ float gain_at(const SynParams& p, long s_abs, int hop)
+{
+    if (s_abs < p.head_len) return __ldg(p.gain_head + s_abs);
+    const long tail0 = p.tl.sig_len - p.tail_len;
+    if (s_abs >= tail0) return __ldg(p.gain_tail + (s_abs - tail0));
+    return __ldg(p.gain_mid + (int)(s_abs % hop));
+}
+
+template <int HS>
+__global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve_smem(smem_raw);
+    const Lanes L = make_lanes();
+    load_tables(s, p.tables, L.t);
+    constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
+    const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
+    const int f0 = tile * p.tl.tile_frames;
+    const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
+    const int npairs = (nf + 1) >> 1;
+    const int tile_len = p.tl.tile_frames * H;
+    const long sbase = (long)f0 * H;
+    float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
+    const long lim = p.tl.sig_len - sbase;
+    const bool has_prev = tile > 0, has_next = (tile + 1) < p.tl.n_tiles;
+    float* __restrict__ hout = p.hb_out + ((long)clip * p.tl.n_tiles + tile) * HALO;
+    const int t = L.t, nfq = p.n_freqs;
+
+    auto st = [&](int row, float val) {
+        const int o = row + t;
+        if (o >= lim) return;
+        if (has_prev && row < HALO) hout[o] = val;                    // head partial
+        else if (has_next && row >= tile_len) sout[o] = val;          // tail partial
+        else sout[o] = val * gain_at(p, sbase + o, H);
+    };
+
+    float acc[NR];
+#pragma unroll
+    for (int j = 0; j < KEEP; j++) acc[j] = 0.0f;
+    __syncthreads();
+
+    for (int pr = 0; pr < npairs; pr++) {
+        const int off0 = pr * 2 * H;
+        const int fA = f0 + 2 * pr;
+        const bool validB = (fA + 1) < p.tl.n_frames;
+#pragma unroll
+        for (int j = KEEP; j < NR; j++) acc[j] = 0.0f;
+
+        // stage the two spectrogram rows (contiguous in memory) into the exchange buffer
+        const float2* __restrict__ src = p.spec + ((long)clip * p.tl.n_frames + fA) * nfq;
+        float2* SA = s.xb;
+        float2* SB = s.xb + 2176;
+        for (int o = t; o < 2 * nfq; o += kThreads) {
+            const int fr = (o >= nfq), e = o - fr * nfq;
+            const float2 x = (fr == 0 || validB) ? __ldg(src + o) : make_float2(0.f, 0.f);
+            (fr ? SB : SA)[e + (e >> 4)] = x;
+        }
+        __syncthreads();
+        // X[j+1] = complex(realm0, realn1) = (entry.y, entry.x); entries >= n_freqs replicate the last
+        // kept one (grow); X[0] = 0; X[2048] keeps only its real part.  Z' = XA + i*XB, scaled by 1/N.
+        float2 v[16];
+        constexpr float inv_n = 1.0f / 4096.0f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int k = L.klow + 256 * j;
+            const int kk = (k <= 2048) ? k : 4096 - k;
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            if (kk >= 1) {
+                int e = kk - 1; e = (e < nfq) ? e : nfq - 1;
+                const float2 ea = SA[e + (e >> 4)], eb = SB[e + (e >> 4)];
+                a = make_float2(ea.y, ea.x); b = make_float2(eb.y, eb.x);
+                if (kk == 2048) { a.y = 0.f; b.y = 0.f; }
+                if (k > 2048) { a.y = -a.y; b.y = -b.y; }
+            }
+            v[j] = make_float2((a.x - b.y) * inv_n, (a.y + b.x) * inv_n);
+        }
+        __syncthreads();     // staging reads done before the inverse transform reuses the buffer
+
+        fft4096_inv(v, s, L);
+
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const float w = s.win[m * 256 + t];
+            acc[m] = fmaf(v[m].x, w, acc[m]);
+            acc[m + HS] = fmaf(v[m].y, w, acc[m + HS]);
+        }
+#pragma unroll
+        for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
+#pragma unroll
+        for (int j = 0; j < KEEP; j++) acc[j] = acc[j + SH];
+        __syncthreads();     // pattern-(a) reads of the inverse done before the next staging writes
+    }
+#pragma unroll
+    for (int j = 0; j < KEEP; j++) st(npairs * 2 * H + j * 256, acc[j]);
+}
+
+// finishes the samples shared by two tiles: sig[s] = (sig[s] + hb[s]) * gain
+__global__ void k_halo_fix(float* __restrict__ sig, const float* __restrict__ hb, Tiling tl, int hop, int halo,
+                           int n_clips, int use_gain, SynParams gp)
+{
+    const long per_clip = (long)(tl.n_tiles - 1) * halo;
+    const long total = per_clip * n_clips;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < total; i += step) {
+        const int clip = (int)(i / per_clip);
+        const long r = i - (long)clip * per_clip;
+        const int tile = (int)(r / halo) + 1, o = (int)(r % halo);
+        const long s_abs = (long)tile * tl.tile_frames * hop + o;
+        if (s_abs >= tl.sig_len) continue;
+        float* d = sig + (long)clip * tl.sig_stride + s_abs;
+        float x = *d + hb[((long)clip * tl.n_tiles + tile) * halo + o];
+        if (use_gain) x *= gain_at(gp, s_abs, hop);
+        *d = x;
+    }
+}
+
+// ------------------------------------------------------------------ K7: Image (dumpbuffer)
+// Replaces mel dumpbuffer (mel/impl.go:16-44) and phase dumpbuffer (phase/impl.go:15-43):
+// per-channel min/max with the reference's sentinels, truncating 8-bit quantisation, float64.
+__global__ void k_minmax_f64(const double* __restrict__ buf, long n_entries, double init_max, double init_min,
+                             double* __restrict__ partial /* [grid][4] */)
+{
+    __shared__ double sm[4][256];
+    double mx0 = init_max, mx1 = init_max, mn0 = init_min, mn1 = init_min;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n_entries; i += step) {
+        const double a = buf[2 * i], b = buf[2 * i + 1];
+        if (a > mx0) mx0 = a;
+        if (a < mn0) mn0 = a;
+        if (b > mx1) mx1 = b;
+        if (b < mn1) mn1 = b;
+    }
+    sm[0][threadIdx.x] = mx0; sm[1][threadIdx.x] = mx1; sm[2][threadIdx.x] = mn0; sm[3][threadIdx.x] = mn1;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            if (sm[0][threadIdx.x + w] > sm[0][threadIdx.x]) sm[0][threadIdx.x] = sm[0][threadIdx.x + w];
+            if (sm[1][threadIdx.x + w] > sm[1][threadIdx.x]) sm[1][threadIdx.x] = sm[1][threadIdx.x + w];
+            if (sm[2][threadIdx.x + w] < sm[2][threadIdx.x]) sm[2][threadIdx.x] = sm[2][threadIdx.x + w];
+            if (sm[3][threadIdx.x + w] < sm[3][threadIdx.x]) sm[3][threadIdx.x] = sm[3][threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int c = 0; c < 4; c++) partial[blockIdx.x * 4 + c] = sm[c][0];
+}
+__global__ void k_minmax_final(const double* __restrict__ partial, int n, double init_max, double init_min,
+                               double* __restrict__ out4)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    double mx0 = init_max, mx1 = init_max, mn0 = init_min, mn1 = init_min;
+    for (int i = 0; i < n; i++) {
+        if (partial[4 * i] > mx0) mx0 = partial[4 * i];
+        if (partial[4 * i + 1] > mx1) mx1 = partial[4 * i + 1];
+        if (partial[4 * i + 2] < mn0) mn0 = partial[4 * i + 2];
+        if (partial[4 * i + 3] < mn1) mn1 = partial[4 * i + 3];
+    }
+    out4[0] = mx0; out4[1] = mx1; out4[2] = mn0; out4[3] = mn1;
+}
+// Go int(f) on amd64 then uint16(): truncation, NaN/overflow -> 0x8000000000000000 -> low bits 0
+__device__ __forceinline__ unsigned go_trunc_u16(double f)
+{
+    if (!(f == f) || f >= 9223372036854775808.0 || f < -9223372036854775808.0) return 0u;
+    return (unsigned)((unsigned long long)(long long)f & 0xffffull);
+}
+__global__ void k_quantise_u16(const double* __restrict__ buf, long n_entries, const double* __restrict__ mm,
+                               unsigned short* __restrict__ out)
+{
+    const double mx0 = mm[0], mx1 = mm[1], mn0 = mm[2], mn1 = mm[3];
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n_entries; i += step) {
+        const double v0 = (buf[2 * i] - mn0) / (mx0 - mn0);
+        const double v1 = (buf[2 * i + 1] - mn1) / (mx1 - mn1);
+        out[i] = (unsigned short)((go_trunc_u16(255 * v0) | (go_trunc_u16(255 * v1) << 8)) & 0xffffu);
+    }
+}
+
+// ------------------------------------------------------------------ K7b: PNG pixel arithmetic
+// Replaces the quantisation loops of mel dumpimage (mel/impl.go:138-181) and phase dumpimage
+// (phase/impl.go:170-266) and the de-quantisation of the two loadpng (mel/impl.go:92-112,
+// phase/impl.go:98-147).  float64 with explicitly un-fused IEEE operations so pixel bytes match
+// the Go float64 arithmetic bit for bit; zlib/PNG container work stays on the host.
+__global__ void k_asinh_passes(double* __restrict__ buf, long n, int passes, int inverse)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        double v = buf[i];
+        for (int p = 0; p < passes; p++) v = inverse ? sinh(v) : asinh(v);
+        buf[i] = v;
+    }
+}
+__device__ __forceinline__ unsigned go_trunc_mask(double f, unsigned long long mask)
+{
+    if (!(f == f) || f >= 9223372036854775808.0 || f < -9223372036854775808.0) return 0u;
+    return (unsigned)((unsigned long long)(long long)f & mask);
+}
+// out3[i] = (R, G, B) for entry i (buffer order x*mels+y); mm = max0,max1,min0,min1
+__global__ void k_quantise_rgb(const double* __restrict__ buf, long n_entries, const double* __restrict__ mm,
+                               int maxval, int blue_wrap, unsigned short* __restrict__ out3)
+{
+    const double mx0 = mm[0], mx1 = mm[1], mn0 = mm[2], mn1 = mm[3], mv = (double)maxval;
+    const unsigned long long mask = (unsigned long long)maxval;      // 255 or 65535: uint8()/uint16() wrap
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n_entries; i += step) {
+        const double v0 = __ddiv_rn(__dsub_rn(buf[2 * i], mn0), __dsub_rn(mx0, mn0));
+        const double v1 = __ddiv_rn(__dsub_rn(buf[2 * i + 1], mn1), __dsub_rn(mx1, mn1));
+        out3[3 * i + 0] = (unsigned short)go_trunc_mask(__dmul_rn(mv, v0), mask);
+        out3[3 * i + 1] = (unsigned short)go_trunc_mask(__dmul_rn(mv, v1), mask);
+        out3[3 * i + 2] = blue_wrap ? (unsigned short)go_trunc_mask(__dmul_rn(mv, -v0), mask) : (unsigned short)0;
+    }
+}
+// rg[i] = (R, G) pixel values (already >>8 for 8-bit images); out[i] = px/maxval*(max-min)+min, then sinh passes
+__global__ void k_dequantise(const unsigned short* __restrict__ rg, long n_entries, double maxval, double mx0,
+                             double mx1, double mn0, double mn1, int passes, double* __restrict__ out)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n_entries; i += step) {
+        double a = __dadd_rn(__dmul_rn(__ddiv_rn((double)rg[2 * i], maxval), __dsub_rn(mx0, mn0)), mn0);
+        double b = __dadd_rn(__dmul_rn(__ddiv_rn((double)rg[2 * i + 1], maxval), __dsub_rn(mx1, mn1)), mn1);
+        for (int p = 0; p < passes; p++) { a = sinh(a); b = sinh(b); }
+        out[2 * i] = a; out[2 * i + 1] = b;
+    }
+}
+
+}  // namespace gomel

@@ -1,0 +1,193 @@
+"""Drop-in for the reference's Python module phase.py (class Phase, phase.py:16-349) and mirror
+of the Go package `phase` (phase/phase.go): same constructor, attributes, method names, shapes
+and error behaviour -- but to_phase / from_phase run on the GPU through the C ABI of
+libgomelcuda.so (ctypes), not in NumPy.
+
+    ph = Phase(sample_rate=48000)
+    spec = ph.to_phase(audio)        # phase.py:113  -> (frames*num_freqs, 2) float64 (Im, Re)
+    audio2 = ph.from_phase(spec)     # phase.py:144  -> float64 waveform
+
+Go-style aliases (NumFreqs, ToPhase, FromPhase, Image ...) are provided for the Go package's
+callers.  Python-vs-Go behavioural differences listed in SURVEY.md Appendix C are kept per
+language (e.g. volume boost applied iff > 0 here, iff != 0 through the Go names).
+"""
+import numpy as np
+
+from . import _lib
+from . import codec
+from .codec import is_padded, pad  # noqa: F401  (module-level helpers of the reference)
+
+
+class Phase:
+    """Phase-preserving spectrogram encoder/decoder (phase.py:16-349)."""
+
+    def __init__(self, sample_rate=None, num_freqs=None, window=1280, resolut=4096, y_reverse=True,
+                 volume_boost=0.0, HDR=False, IHS=False, device=0):
+        self.sample_rate = sample_rate
+        self.window = window
+        self.resolut = resolut
+        self.y_reverse = y_reverse
+        self.volume_boost = volume_boost
+        self.HDR = HDR
+        self.IHS = 0 if HDR else 2 if IHS else 0          # phase.py:41
+        self.num_freqs = 0                                # "bad defaults", phase.py:43
+        self.family = None
+        self.device = device
+        if sample_rate is not None:
+            self.reconfigure_sr(sample_rate)
+        if num_freqs is not None and sample_rate is None:
+            self.num_freqs = num_freqs                    # extension: explicit NumFreqs like the Go struct
+
+    # ---- configuration (phase.py:49-111)
+    def reconfigure_sr(self, sample_rate):
+        if sample_rate in [8000, 16000, 24000, 32000, 48000]:
+            self.num_freqs = 768 * 2 if self.HDR else 768
+            self.family = True
+        elif sample_rate in [11025, 22050, 44100]:
+            self.num_freqs = 836 * 2 if self.HDR else 836
+            self.family = False
+        else:
+            raise ValueError(
+                f"Unsupported sample rate: {sample_rate}. "
+                f"Supported rates are: 8000, 16000, 24000, 32000, 48000, 11025, 22050, 44100")
+
+    def pad_shift(self, sample_rate):
+        table = ({48000: (0, 0), 32000: (2, 1), 24000: (1, 1), 16000: (1, 2), 8000: (1, 5)} if self.family
+                 else {44100: (0, 0), 22050: (1, 1), 11025: (1, 3)})
+        if sample_rate in table:
+            return table[sample_rate]
+        raise ValueError("Unsupported sample_ratePlease configure sample_rate to Phase")
+
+    def zero_pad(self, sr):
+        return self.pad_shift(sr)[0]
+
+    def zero_shift(self, sr):
+        return self.pad_shift(sr)[1]
+
+    # ---- GPU transforms
+    def _cfg(self, boost):
+        return _lib.make_config(n_fft=self.resolut, hop=self.window, n_mels=0, n_freqs=self.num_freqs,
+                                gl_iters=0, volume_boost=boost)
+
+    def to_phase(self, audio_buffer):
+        """phase.py:113-142 / phase.ToPhase (phase/phase.go:41-70)"""
+        return _lib.default_context(self.device).to_phase(self._cfg(0.0), audio_buffer)
+
+    def from_phase(self, spectrogram):
+        """phase.py:144-220: volume boost applied iff > 0 (phase.py:216)"""
+        boost = self.volume_boost if self.volume_boost > 0 else 0.0
+        return _lib.default_context(self.device).from_phase(self._cfg(boost), spectrogram)
+
+    # ---- file API (phase.py:222-349)
+    def _prepare(self, audio, sample_rate, update_rate):
+        self.reconfigure_sr(sample_rate=sample_rate)
+        zp, zs = self.zero_pad(sample_rate), self.zero_shift(sample_rate)
+        if zp > 0:
+            original_len = len(audio)
+            audio = zero_stuff_upsample(audio, zp, zs)
+            if update_rate:
+                sample_rate = int(sample_rate * len(audio) / original_len)
+        return audio, sample_rate
+
+    def to_phase_wav(self, input_file, output_file):
+        audio, sample_rate = load_wav_with_sr(input_file)
+        audio, sample_rate = self._prepare(audio, sample_rate, update_rate=False)      # phase.py:234-240
+        original_length = len(audio)
+        spectrogram = self.to_phase(audio)
+        samples_in_mel = float(original_length * self.num_freqs) / float(len(spectrogram))
+        save_image(output_file, spectrogram, self.num_freqs, samples_in_mel, sample_rate, self.y_reverse,
+                   self.HDR, self.IHS, device=self.device)
+
+    def to_wav_png(self, input_file, output_file):
+        spectrogram, samples, embedded_sample_rate, self.num_freqs = load_image(
+            input_file, self.y_reverse, self.HDR, self.IHS, device=self.device)
+        audio = self.from_phase(spectrogram)
+        main_rate = 48000 if self.num_freqs in [768, 768 * 2] else 44100
+        standard_rates = [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000]
+        sample_rate = min(standard_rates, key=lambda x: abs(x - embedded_sample_rate))
+        original_length = int(samples)
+        if len(audio) > original_length > 0:
+            audio = audio[:original_length]
+        save_wav(output_file, audio, main_rate)
+        return sample_rate
+
+    # ---- Go package `phase` names (phase/phase.go)
+    @property
+    def NumFreqs(self):
+        return self.num_freqs
+
+    @NumFreqs.setter
+    def NumFreqs(self, v):
+        self.num_freqs = v
+
+    def ToPhase(self, buf):
+        """phase.ToPhase (phase/phase.go:41-70)"""
+        return self.to_phase(buf)
+
+    def FromPhase(self, ospectrum):
+        """phase.FromPhase (phase/phase.go:136-153): boost applied iff != 0 (phase/phase.go:146)"""
+        return _lib.default_context(self.device).from_phase(self._cfg(self.volume_boost), ospectrum)
+
+    def Image(self, buf):
+        """Phase.Image (phase/phase.go:190-192) -> dumpbuffer (phase/impl.go:15-43)"""
+        return _lib.default_context(self.device).image(buf, self.num_freqs)
+
+    def ihsPasses(self):
+        """phase/phase.go:31-36"""
+        return 2 if (self.IHS and not self.HDR) else 0
+
+
+def NewPhase():
+    """phase.NewPhase (phase/phase.go:21-28): NumFreqs 768, Window 1280, Resolut 4096, VolumeBoost 0"""
+    p = Phase(num_freqs=768, y_reverse=False)
+    return p
+
+
+# ---------------------------------------------------------------- module helpers (phase.py:352-852)
+def shrink(spectrogram, resolut, num_freqs):
+    """phase.py:430-435 / shrink (phase/impl.go:383-391)"""
+    original_bins = resolut // 2
+    spectrogram = np.asarray(spectrogram)
+    time_frames = len(spectrogram) // original_bins
+    return spectrogram.reshape(time_frames, original_bins, 2)[:, :num_freqs, :].reshape(-1, 2)
+
+
+def grow(spectrogram, resolut, num_freqs):
+    """phase.py:438-466 / grow (phase/impl.go:392-403): replicate the last kept bin upward"""
+    target_bins = resolut // 2
+    s = np.asarray(spectrogram).reshape(-1, num_freqs, 2)
+    rep = np.repeat(s[:, -1:, :], target_bins - num_freqs, axis=1)
+    return np.concatenate([s, rep], axis=1).reshape(-1, 2)
+
+
+def zero_stuff_upsample(audio, zero_pad, zero_shift):
+    """phase.py:503-549 / zeroStuffUpsample (phase/impl.go:509-529)"""
+    if zero_pad == 0:
+        return audio
+    audio = np.asarray(audio)
+    n = len(audio)
+    num_groups = (n + zero_pad - 1) // zero_pad
+    output = np.zeros(n + num_groups * zero_shift, dtype=audio.dtype)
+    i = np.arange(n)
+    output[i + (i // zero_pad) * zero_shift] = audio * (1 + zero_shift)
+    return output
+
+
+def load_wav_with_sr(file_path):
+    a, sr = codec.load_wav(file_path)
+    return a, int(sr)
+
+
+def load_wav(file_path):
+    return codec.load_wav(file_path)[0]
+
+
+def save_wav(file_path, audio_buffer, sample_rate):
+    """phase.py:589-601: clip to [-1,1], 16-bit PCM mono"""
+    codec.save_wav(file_path, audio_buffer, sample_rate)
+
+
+pack_float16_to_bytes = codec.pack_f16_py
+unpack_bytes_to_float64 = codec.unpack_f16
+save_image = codec.phase_save_image_py
+load_image = codec.phase_load_image_py

@@ -1,0 +1,159 @@
+/*
+ * gomel_cuda.h -- C ABI of libgomelcuda.so, the B200 (sm_100a) implementation of the gomel
+ * spectrogram hot path.  Plain pointers and sizes only: this is what the reference's Go packages
+ * bind through cgo (INTEGRATION.md shows the stub) and what gomel_b200/*.py bind through ctypes.
+ *
+ * The reference (neurlang/gomel) has no FFI of its own; each entry point below names the Go
+ * function whose arithmetic it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative gomel_status; gomel_last_error(ctx)
+ *     returns a message for the last failure on that context.
+ *   - the caller allocates every output; the library never retains caller memory after return.
+ *   - a context owns one device, one stream and grow-only scratch; calls on one context are
+ *     serialised by an internal mutex and may come from any OS thread (cgo hops threads).
+ *   - this build supports Resolut (n_fft) = 4096 and Window (hop) = 1280 (the configuration of
+ *     cmd/tomel, cmd/towav, cmd/tophase, cmd/fromphase and of NewPhase); anything else returns
+ *     GOMEL_E_UNSUPPORTED.  There is NO CPU fallback.
+ */
+#ifndef GOMEL_CUDA_H
+#define GOMEL_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gomel_ctx gomel_ctx;
+
+typedef enum {
+    GOMEL_OK = 0,
+    GOMEL_E_ARG = -1,          /* bad argument, incl. len % n_mels != 0 where Go panics (mel/impl.go:366-372) */
+    GOMEL_E_CUDA = -2,         /* CUDA runtime error */
+    GOMEL_E_NOMEM = -3,        /* device or pinned allocation failed */
+    GOMEL_E_UNSUPPORTED = -4,  /* configuration outside this build (n_fft != 4096, hop != 1280) */
+    GOMEL_E_STATE = -5         /* call order, e.g. mel tables not set */
+} gomel_status;
+
+/* The fields of mel.Mel (mel/mel.go:10-27) and phase.Phase (phase/phase.go:8-18) that reach
+ * arithmetic.  YReverse / SampleRate / IHS / HDR only affect the PNG/WAV codecs on the host. */
+typedef struct {
+    int n_fft;           /* Resolut */
+    int hop;             /* Window  */
+    int n_mels;          /* NumMels */
+    int n_freqs;         /* NumFreqs */
+    int gl_iters;        /* GriffinLimIterations */
+    double tune_mul;     /* TuneMul */
+    double tune_add;     /* TuneAdd */
+    double volume_boost; /* VolumeBoost (phase: multiplicative, applied iff != 0) */
+    int flags;           /* reserved, 0 */
+} gomel_config;
+
+/* ---- context ------------------------------------------------------------------------- */
+int  gomel_ctx_create(int device, gomel_ctx **out);
+void gomel_ctx_destroy(gomel_ctx *ctx);
+const char *gomel_last_error(gomel_ctx *ctx);
+const char *gomel_version(void);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+unsigned long long gomel_launch_count(gomel_ctx *ctx);
+/* frames per tile for the tiled kernels; 0 = automatic (default) */
+int  gomel_set_tile_frames(gomel_ctx *ctx, int tile_frames);
+
+/* ---- sizing: pad (mel/impl.go:429-455) + gossp NumFrames + ISTFT length (mel/mel.go:79) --- */
+int  gomel_frames(const gomel_config *cfg, long n_samples, long *n_padded, long *n_frames, long *ola_len);
+long gomel_ola_len(const gomel_config *cfg, long n_frames);
+
+/* ---- mel filterbank tables ---------------------------------------------------------------
+ * The per-band values domel (mel/impl.go:313-323) and undomel (:350-360) derive: int(inlo),
+ * int(inhi), modlo.  Computed by the CALLER's math library (Go's math.Exp/Log in the cgo
+ * binding) because two edges are 1-ulp fragile (SURVEY.md hard part 4); the library never
+ * evaluates exp/log for table construction.  fwd_*: n_mels entries; inv_*: n_fft/2 entries. */
+int  gomel_set_mel_tables(gomel_ctx *ctx, const gomel_config *cfg,
+                          const int *fwd_lo, const int *fwd_hi, const double *fwd_mod,
+                          const int *inv_lo, const int *inv_hi, const double *inv_mod);
+
+/* ---- host-buffer API (what the Go / Python wrappers call; float64 like the reference) ---- */
+/* mel.ToMel (mel/mel.go:46-74): wav[n] -> mel_out[frames*n_mels*2] */
+int  gomel_to_mel(gomel_ctx *ctx, const gomel_config *cfg, const double *wav, long n, double *mel_out);
+/* mel.FromMel (mel/mel.go:142-152): mel[n_frames*n_mels*2] -> wav_out[ola_len].
+ * init_signal (ola_len doubles) replaces rand.Float64() of mel/mel.go:80-83; if NULL the
+ * library fills U[0,1) on the device from `seed`.  The input is NOT modified: the wrapper
+ * applies the reference's in-place exp side effect (mel/impl.go:421-427) itself. */
+int  gomel_from_mel(gomel_ctx *ctx, const gomel_config *cfg, const double *mel, long n_frames,
+                    const double *init_signal, unsigned long long seed, double *wav_out);
+/* phase.ToPhase (phase/phase.go:41-70): wav[n] -> out[frames*n_freqs*2] = (Im X[j+1], Re X[j+1]) */
+int  gomel_to_phase(gomel_ctx *ctx, const gomel_config *cfg, const double *wav, long n, double *out);
+/* phase.FromPhase (phase/phase.go:136-153): spec[n_frames*n_freqs*2] -> wav_out[ola_len] */
+int  gomel_from_phase(gomel_ctx *ctx, const gomel_config *cfg, const double *spec, long n_frames, double *wav_out);
+/* Mel.Image / Phase.Image (mel/mel.go:171-173 -> mel/impl.go:16-44; phase/phase.go:190-192 ->
+ * phase/impl.go:15-43): buf[n_entries*2] -> out[n_entries]; minmax_out (optional) = max0,max1,min0,min1 */
+int  gomel_image(gomel_ctx *ctx, const double *buf, long n_entries, int mels, unsigned short *out, double *minmax_out);
+
+/* ---- PNG pixel arithmetic (float64 on the device; the PNG/zlib container stays on the host) ----
+ * gomel_quantise: the quantisation loops of mel dumpimage (mel/impl.go:138-181) and phase
+ * dumpimage (phase/impl.go:170-266).  buf[n_entries*2] is left untouched; `ihs_passes` asinh
+ * passes (phase/impl.go:171-177) are applied to a device copy first.
+ *   flags: GOMEL_Q_SINGLE_MINMAX  one min/max over both channels (mel)  else per channel (phase)
+ *          GOMEL_Q_HDR            maxVal 65535 (uint16 wrap) else 255 (uint8 wrap)
+ *          GOMEL_Q_BLUE_WRAP      B = uintN(int(maxVal * (-val0)))  (phase/impl.go:229,256) else 0
+ * rgb_out[n_entries*3] in buffer order (x*mels + y); minmax_out = max0,max1,min0,min1 (after asinh),
+ * which the caller packs into the float16 metadata bytes. */
+#define GOMEL_Q_SINGLE_MINMAX 1
+#define GOMEL_Q_HDR 2
+#define GOMEL_Q_BLUE_WRAP 4
+int  gomel_quantise(gomel_ctx *ctx, const double *buf, long n_entries, int mels, int flags, int ihs_passes,
+                    unsigned short *rgb_out, double *minmax_out);
+/* gomel_dequantise: loadpng (mel/impl.go:92-112, phase/impl.go:98-147): rg[n_entries*2] pixel
+ * values (0..255 or 0..65535) -> out[n_entries*2] = px/maxVal*(max-min)+min, then `ihs_passes` sinh. */
+int  gomel_dequantise(gomel_ctx *ctx, const unsigned short *rg, long n_entries, int hdr, double max0,
+                      double max1, double min0, double min1, int ihs_passes, double *out);
+
+/* ---- device-resident API (float32 buffers in HBM; no host synchronisation unless stated) ---- */
+int  gomel_dev_malloc(gomel_ctx *ctx, size_t bytes, void **out);
+int  gomel_dev_free(gomel_ctx *ctx, void *p);
+int  gomel_host_malloc(gomel_ctx *ctx, size_t bytes, void **out);     /* pinned */
+int  gomel_host_free(gomel_ctx *ctx, void *p);
+int  gomel_copy_h2d(gomel_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async on ctx stream */
+int  gomel_copy_d2h(gomel_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async on ctx stream */
+int  gomel_sync(gomel_ctx *ctx);
+/* CUDA-event timer on the context's stream (the stream every kernel of the context runs on) */
+int  gomel_timer_start(gomel_ctx *ctx);
+int  gomel_timer_stop(gomel_ctx *ctx, float *ms);                     /* records, synchronises */
+/* device time of the dominant kernel of the LAST transform issued on this context (all
+ * Griffin-Lim iteration launches of a FromMel, or the STFT launch of a ToMel/ToPhase), measured
+ * by CUDA events recorded around those launches on the context's stream; *launches = how many. */
+int  gomel_last_hot_kernel_ms(gomel_ctx *ctx, float *ms, int *launches);
+
+/* Batched STFT + mel (K1+K2).  d_sig: [n_clips][sig_stride] float32, each clip zero padded to
+ * n_padded = sig_len samples; d_mel: [n_clips][n_frames][n_mels][2] float32 (natural log). */
+int  gomel_to_mel_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_sig, int n_clips,
+                      long sig_stride, long sig_len, long n_frames, float *d_mel);
+/* Batched STFT + phase representation (K1+K4). d_out: [n_clips][n_frames][n_freqs][2] */
+int  gomel_to_phase_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_sig, int n_clips,
+                        long sig_stride, long sig_len, long n_frames, float *d_out);
+/* Batched half spectra (tests): d_spec [n_clips][n_frames][2049][2] (Re, Im) */
+int  gomel_stft_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_sig, int n_clips,
+                    long sig_stride, long sig_len, long n_frames, float *d_spec);
+/* Batched FromMel (K3 + iters x K5).  d_mel as above; d_init/d_out: [n_clips][sig_stride] with
+ * sig_stride >= ola_len; d_init may be NULL (device U[0,1) from seed).  d_init is not modified. */
+int  gomel_from_mel_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_mel, int n_clips,
+                        long n_frames, const float *d_init, unsigned long long seed,
+                        long sig_stride, float *d_out);
+/* Batched FromPhase (K4+K6). d_spec: [n_clips][n_frames][n_freqs][2]; d_out: [n_clips][sig_stride] */
+int  gomel_from_phase_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_spec, int n_clips,
+                          long n_frames, long sig_stride, float *d_out);
+
+/* ---- pipelined host batch (end-to-end: pinned host float32 in, float32 out, H2D/compute/D2H
+ * overlapped chunk by chunk on three streams).  mel: [n_clips][n_frames*n_mels*2],
+ * init: [n_clips][ola_len] or NULL, out: [n_clips][ola_len]. */
+int  gomel_from_mel_batch_host(gomel_ctx *ctx, const gomel_config *cfg, const float *mel, int n_clips,
+                               long n_frames, const float *init, unsigned long long seed, float *out,
+                               int clips_per_chunk);
+/* wav: [n_clips][n_samples] -> mel_out: [n_clips][n_frames*n_mels*2] */
+int  gomel_to_mel_batch_host(gomel_ctx *ctx, const gomel_config *cfg, const float *wav, int n_clips,
+                             long n_samples, float *mel_out, int clips_per_chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

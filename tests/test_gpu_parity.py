@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the drop-in classes,
+against the float64 CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  STFT / mel magnitudes   <= 1e-5 relative L2
+  Griffin-Lim waveforms   <= 1e-4 relative L2 at equal iteration count, same start signal
+  Image / PNG bytes       bit-exact given identical float64 input; <= 1 LSB on boundary pixels otherwise
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from util import rel_l2, synth_clip
+
+pytestmark = pytest.mark.gpu
+
+TOL_STFT = 1e-5
+TOL_GL = 1e-4
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "phase_ref.npz")
+
+
+def mel_cfg(lib, iters=2):
+    return lib.make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=iters)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from gomel_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def mctx(ctx, lib):
+    ctx.set_mel_tables(mel_cfg(lib), 0.0, 16000.0)
+    return ctx
+
+
+# ------------------------------------------------------------------ K1: STFT
+@pytest.mark.parametrize("seconds,tile", [(1.0, 0), (1.0, 4), (2.3, 6), (0.1, 0)])
+def test_stft_spectrum(mctx, lib, oracle, seconds, tile):
+    cfg = mel_cfg(lib)
+    wav = synth_clip(3, seconds)
+    npad, fr, _ = lib.frames(cfg, len(wav))
+    x = np.zeros(npad, np.float32)
+    x[:len(wav)] = wav
+    d_sig = mctx.dev_malloc(x.nbytes)
+    d_out = mctx.dev_malloc(fr * 2049 * 8)
+    mctx.h2d(d_sig, x)
+    mctx.set_tile_frames(tile)
+    mctx.check(mctx.lib.gomel_stft_dev(mctx.h, C.byref(cfg), d_sig, 1, npad, npad, fr, d_out))
+    mctx.set_tile_frames(0)
+    got = np.empty((fr, 2049, 2), np.float32)
+    mctx.d2h(got, d_out)
+    mctx.dev_free(d_sig)
+    mctx.dev_free(d_out)
+    w = oracle.hann(4096)
+    xp = x.astype(np.float64)
+    ref = np.stack([np.fft.rfft(xp[i * 1280:i * 1280 + 4096] * w) for i in range(fr)])
+    o0 = oracle.fft(xp[:4096] * w)[:2049]                 # the oracle's own radix-2 on frame 0
+    assert rel_l2(ref[0], o0) < 1e-13
+    gotc = got[..., 0] + 1j * got[..., 1]
+    err = np.linalg.norm(gotc - ref) / np.linalg.norm(ref)
+    assert err < TOL_STFT, err
+
+
+# ------------------------------------------------------------------ ToMel
+@pytest.mark.parametrize("clip,seconds,tile", [(0, 10.0, 0), (1, 1.0, 4), (2, 0.05, 0), (5, 3.7, 10)])
+def test_to_mel(mctx, lib, oracle, clip, seconds, tile):
+    from gomel_b200 import NewMel
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut = 192, 0, 16000, 1280, 4096
+    wav = synth_clip(clip, seconds)
+    mctx.set_tile_frames(tile)
+    got = m.ToMel(wav)
+    mctx.set_tile_frames(0)
+    ref = oracle.to_mel(oracle.config(), wav)
+    assert got.shape == ref.shape
+    assert rel_l2(np.exp(got), np.exp(ref)) < TOL_STFT        # linear mel magnitudes
+    assert rel_l2(got, ref) < TOL_STFT                         # log domain
+
+
+def test_to_mel_adversarial(mctx, lib, oracle):
+    from gomel_b200 import NewMel
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut = 192, 0, 16000, 1280, 4096
+    rng = np.random.default_rng(7)
+    noise = rng.uniform(-1, 1, 44100)
+    got, ref = m.ToMel(noise), oracle.to_mel(oracle.config(), noise)
+    assert rel_l2(np.exp(got), np.exp(ref)) < TOL_STFT
+    zeros = np.zeros(30000)
+    got, ref = m.ToMel(zeros), oracle.to_mel(oracle.config(), zeros)
+    assert np.allclose(got, ref, rtol=0, atol=2e-6)             # ln(1e-5) everywhere
+    imp = np.zeros(25000)
+    imp[5000] = 1.0
+    got, ref = m.ToMel(imp), oracle.to_mel(oracle.config(), imp)
+    assert rel_l2(np.exp(got), np.exp(ref)) < TOL_STFT
+
+
+# ------------------------------------------------------------------ FromMel (Griffin-Lim)
+def _from_mel_case(mctx, oracle, clip, seconds, iters, tile, seed):
+    from gomel_b200 import NewMel
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut = 192, 0, 16000, 1280, 4096
+    m.GriffinLimIterations = iters
+    wav = synth_clip(clip, seconds)
+    ocfg = oracle.config(gl_iters=iters)
+    mel = oracle.to_mel(ocfg, wav)
+    frames = len(mel) // 192
+    init = np.random.default_rng(seed).random(4096 + (frames - 1) * 1280)
+    m.InitSignal = init
+    mctx.set_tile_frames(tile)
+    got = m.FromMel(mel.copy())
+    mctx.set_tile_frames(0)
+    ref = oracle.from_mel(ocfg, mel, init)
+    return got, ref
+
+
+@pytest.mark.parametrize("seconds,iters,tile", [(0.3, 0, 0), (0.3, 1, 0), (0.3, 2, 4), (1.0, 2, 0), (1.0, 3, 6),
+                                                (1.0, 8, 8), (0.45, 2, 4)])
+def test_from_mel_small(mctx, oracle, seconds, iters, tile):
+    got, ref = _from_mel_case(mctx, oracle, 11, seconds, iters, tile, 5000)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < TOL_GL, rel_l2(got, ref)
+
+
+def test_from_mel_32_iterations(mctx, oracle):
+    got, ref = _from_mel_case(mctx, oracle, 12, 1.5, 32, 8, 5001)
+    assert rel_l2(got, ref) < TOL_GL, rel_l2(got, ref)
+
+
+def test_from_mel_tiling_is_deterministic(mctx, oracle):
+    a, _ = _from_mel_case(mctx, oracle, 13, 1.0, 4, 4, 5002)
+    b, _ = _from_mel_case(mctx, oracle, 13, 1.0, 4, 4, 5002)
+    assert np.array_equal(a, b)
+
+
+def test_from_mel_mutates_input_like_reference(mctx, oracle):
+    from gomel_b200 import NewMel
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut = 192, 0, 16000, 1280, 4096
+    mel = oracle.to_mel(oracle.config(), synth_clip(1, 0.3))
+    before = mel.copy()
+    m.FromMel(mel)
+    assert np.allclose(mel, np.exp(before), rtol=1e-15)        # mel/impl.go:421-427 side effect
+
+
+def test_from_mel_bad_length_is_an_error(mctx, lib):
+    bad = np.zeros((192 * 3 + 48, 2))
+    with pytest.raises(lib.GomelError):
+        mctx.from_mel(mel_cfg(lib), bad)                        # the Go reference panics here
+
+
+def test_unsupported_config_fails_loudly(mctx, lib):
+    from gomel_b200 import NewMel
+    m = NewMel()                                                # NewMel defaults: Window 256, Resolut 2048
+    with pytest.raises(lib.GomelError) as e:
+        m.ToMel(np.zeros(10000))
+    assert e.value.code == lib.E_UNSUPPORTED
+
+
+# ------------------------------------------------------------------ phase
+@pytest.mark.parametrize("nf", [768, 836, 1536, 2048, 5])
+def test_to_phase(ctx, lib, oracle, nf):
+    from gomel_b200 import Phase
+    ph = Phase(num_freqs=nf)
+    wav = synth_clip(21, 1.3)
+    got = ph.to_phase(wav)
+    ref = oracle.to_phase(oracle.config(num_freqs=nf), wav)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < TOL_STFT
+
+
+@pytest.mark.parametrize("nf,seconds,tile,boost", [(768, 1.3, 0, 0.0), (768, 1.3, 4, 1.666), (836, 0.2, 0, 0.0),
+                                                   (1536, 2.0, 6, 0.0), (2048, 0.6, 0, 0.0), (768, 10.0, 0, 0.0)])
+def test_from_phase(ctx, lib, oracle, nf, seconds, tile, boost):
+    from gomel_b200 import Phase
+    ph = Phase(num_freqs=nf, volume_boost=boost)
+    wav = synth_clip(22, seconds)
+    ocfg = oracle.config(num_freqs=nf, volume_boost=boost)
+    spec = oracle.to_phase(ocfg, wav)
+    ctx.set_tile_frames(tile)
+    got = ph.from_phase(spec)
+    ctx.set_tile_frames(0)
+    ref = oracle.from_phase(ocfg, spec)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < TOL_STFT, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("frames", [1, 2, 3, 4, 5, 7, 16, 17, 18])
+def test_from_phase_frame_counts(ctx, lib, oracle, frames):
+    from gomel_b200 import Phase
+    rng = np.random.default_rng(frames)
+    spec = rng.standard_normal((frames * 768, 2))
+    got = Phase(num_freqs=768).from_phase(spec)
+    ref = oracle.from_phase(oracle.config(num_freqs=768), spec)
+    assert rel_l2(got, ref) < TOL_STFT
+
+
+def test_phase_against_reference_golden(ctx, lib):
+    """outputs of the reference's own phase.py (tests/golden/make_golden.py)"""
+    from gomel_b200 import Phase
+    g = np.load(GOLD)
+    for name, sr in (("a48k", 48000), ("b44k", 44100), ("c48k_short", 48000)):
+        ph = Phase(sample_rate=sr)
+        assert ph.num_freqs == int(g[f"{name}_num_freqs"])
+        spec = ph.to_phase(g[f"{name}_wav"])
+        assert spec.shape == g[f"{name}_spec"].shape
+        assert rel_l2(spec, g[f"{name}_spec"]) < TOL_STFT
+        rec = ph.from_phase(g[f"{name}_spec"])
+        assert rel_l2(rec, g[f"{name}_rec"]) < TOL_STFT
+    ph = Phase(sample_rate=48000, volume_boost=1.666)
+    assert rel_l2(ph.from_phase(g["a48k_spec"]), g["a48k_rec_boost"]) < TOL_STFT
+    ph = Phase(sample_rate=48000, HDR=True)
+    assert ph.num_freqs == int(g["hdr_num_freqs"])
+    assert rel_l2(ph.to_phase(g["hdr_wav"]), g["hdr_spec"]) < TOL_STFT
+    assert rel_l2(ph.from_phase(g["hdr_spec"]), g["hdr_rec"]) < TOL_STFT
+
+
+# ------------------------------------------------------------------ Image / PNG pixel arithmetic
+def test_image_bit_exact(mctx, lib, oracle):
+    from gomel_b200 import NewMel, Phase
+    rng = np.random.default_rng(3)
+    mel = oracle.to_mel(oracle.config(), synth_clip(4, 1.0))
+    m = NewMel()
+    m.NumMels = 192
+    assert np.array_equal(m.Image(mel), oracle.mel_image(mel, 192))
+    spec = rng.standard_normal((768 * 9, 2)) * 50
+    assert np.array_equal(Phase(num_freqs=768).Image(spec), oracle.phase_image(spec, 768))
+    const = np.full((192 * 4, 2), 3.06e-5)                      # max == min -> NaN -> 0
+    assert np.array_equal(m.Image(const), oracle.mel_image(const, 192))
+
+
+@pytest.mark.parametrize("hdr,ihs", [(False, 0), (False, 2), (True, 0)])
+def test_quantise_dequantise_bit_exact(ctx, lib, oracle, hdr, ihs):
+    rng = np.random.default_rng(11)
+    spec = rng.standard_normal((768 * 6, 2)) * 30
+    flags = lib.Q_BLUE_WRAP | (lib.Q_HDR if hdr else 0)
+    rgb, mm = ctx.quantise(spec, 768, flags, ihs)
+    ref = oracle.phase_quantise(spec, 768, False, 1289.4, 48000.0, ihs, hdr)     # (mels, stride, 4)
+    ref_rgb = ref[:, :, :3].transpose(1, 0, 2).reshape(-1, 3).astype(np.uint16)
+    meta = np.zeros(len(ref_rgb), bool)
+    meta[768 - 16:768] = True                                   # x = 0 metadata rows of the blue channel
+    diff = np.abs(rgb.astype(np.int64) - ref_rgb.astype(np.int64))
+    diff[meta, 2] = 0
+    if ihs == 0:
+        assert diff.max() == 0
+    else:                                                       # asinh differs by ulps between libms
+        assert diff[:, :2].max() <= 1 and (diff[:, :2] > 0).mean() < 1e-3
+    # mel variant: single min/max
+    mel = oracle.to_mel(oracle.config(), synth_clip(4, 0.5))
+    rgb, mm = ctx.quantise(mel, 192, lib.Q_SINGLE_MINMAX)
+    ref = oracle.mel_quantise(mel, 192, False, 1289.4, 44100.0)
+    assert np.array_equal(rgb[:, :2], ref[:, :, :2].transpose(1, 0, 2).reshape(-1, 2).astype(np.uint16))
+    # dequantise
+    buf_o, _, _ = oracle.mel_dequantise(ref, False)
+    got = ctx.dequantise(ref[:, :, :2].transpose(1, 0, 2).reshape(-1, 2), False,
+                         oracle.f16_value(oracle.f16_bits(mm[0])), oracle.f16_value(oracle.f16_bits(mm[0])),
+                         oracle.f16_value(oracle.f16_bits(mm[2])), oracle.f16_value(oracle.f16_bits(mm[2])))
+    assert np.array_equal(got, buf_o)
+
+
+# ------------------------------------------------------------------ batched device API + pipelined host batch
+def test_batch_from_mel_matches_single(mctx, lib, oracle):
+    cfg = mel_cfg(lib, iters=3)
+    n_clips, seconds = 5, 0.6
+    mels, inits, refs = [], [], []
+    for c in range(n_clips):
+        mel = oracle.to_mel(oracle.config(), synth_clip(30 + c, seconds))
+        frames = len(mel) // 192
+        ola = 4096 + (frames - 1) * 1280
+        init = np.random.default_rng(60 + c).random(ola)
+        mels.append(mel)
+        inits.append(init)
+        refs.append(oracle.from_mel(oracle.config(gl_iters=3), mel, init))
+    mel32 = np.stack(mels).astype(np.float32)
+    init32 = np.stack(inits).astype(np.float32)
+    out = np.empty((n_clips, ola), np.float32)
+    mctx.check(mctx.lib.gomel_from_mel_batch_host(
+        mctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), n_clips, frames,
+        init32.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_void_p), 2))
+    for c in range(n_clips):
+        assert rel_l2(out[c], refs[c]) < TOL_GL
+
+
+def test_batch_to_mel_matches_oracle(mctx, lib, oracle):
+    cfg = mel_cfg(lib)
+    n_clips, n = 7, 30000
+    wav = np.stack([synth_clip(40 + c, n=n) for c in range(n_clips)]).astype(np.float32)
+    _, fr, _ = lib.frames(cfg, n)
+    out = np.empty((n_clips, fr * 192, 2), np.float32)
+    mctx.check(mctx.lib.gomel_to_mel_batch_host(mctx.h, C.byref(cfg), wav.ctypes.data_as(C.c_void_p), n_clips, n,
+                                               out.ctypes.data_as(C.c_void_p), 3))
+    for c in range(n_clips):
+        ref = oracle.to_mel(oracle.config(), wav[c].astype(np.float64))
+        assert rel_l2(np.exp(out[c]), np.exp(ref)) < TOL_STFT
+
+
+def test_launch_counter_counts_kernels(mctx, lib, oracle):
+    before = mctx.launch_count()
+    from gomel_b200 import Phase
+    Phase(num_freqs=768).to_phase(synth_clip(1, 0.2))
+    assert mctx.launch_count() > before
