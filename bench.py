@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the gomel_b200 hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W          # product arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...          # reference arm: the CPU float64 port of
+                                                           # the Go path (oracle/), all host threads
+
+Metric (BASELINE.json): mel->wav audio-seconds per second, Griffin-Lim 32 iterations, 192 mels,
+Resolut 4096, Window 1280, on 1024 synthetic 10 s 44.1 kHz clips per GPU (configs[3]); clips are
+sharded across ranks with no data-path collective (weak scaling: 1024 clips on every rank).
+A step = one FromMel over the rank's whole batch: K3 (mel -> target magnitudes), 32 launches of
+the Griffin-Lim iteration kernel, the tile-boundary fix-up.
+
+  value     device-resident: mel spectrograms already in HBM when the timed region starts
+  e2e       the same metric through the C ABI call gomel_from_mel_batch_host with PINNED HOST
+            buffers: H2D of the mel batch and D2H of the waveforms inside the timed region
+  roofline  the Griffin-Lim iteration kernel against the measured HBM copy bandwidth
+  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SR = 44100
+N_FFT, HOP, N_MELS, GL_ITERS = 4096, 1280, 192, 32
+CLIP_SECONDS = 10.0
+CLIPS_PER_GPU = 1024
+BASE_CLIPS = 32                      # distinct spectrograms, tiled to CLIPS_PER_GPU
+BYTES_PER_FRAME_ITER = 18436         # 2049*4 magnitudes + 1280*4 read + 1280*4 write
+BYTES_PER_FRAME_ONCE = 9732          # K3: read mel 1536 + write magnitudes 8196
+METRIC = "mel2wav_griffinlim32_audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:                      # region shorter than one sample: take the nearest rows
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ------------------------------------------------------------------------------- reference arm
+def cpu_reference(n_threads, seconds_per_clip, steps, warmup):
+    """Times the oracle port of mel.FromMel (GL 32) on n_threads clips in parallel (OpenMP)."""
+    from oracle import oracle as O
+    from util import synth_clip
+    cfg = O.config(num_mels=N_MELS, window=HOP, resolut=N_FFT, gl_iters=GL_ITERS)
+    base = O.to_mel(cfg, synth_clip(0, seconds_per_clip))
+    frames = len(base) // N_MELS
+    ola = N_FFT + (frames - 1) * HOP
+    mel = np.stack([base] * n_threads)
+    init = np.random.default_rng(5000).random((n_threads, ola))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.from_mel_batch(cfg, mel, init, threads=n_threads)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    audio_s = n_threads * frames * HOP / SR
+    return audio_s * len(times) / sum(times), frames, float(np.mean(times))
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    total_steps = args.steps + args.warmup
+    # ~1.9 CPU-seconds per audio-second per core for GL-32: keep the whole run to a few minutes
+    seconds = float(min(CLIP_SECONDS, max(1.0, 150.0 / max(total_steps, 1) / 1.9)))
+    value, frames, step_s = cpu_reference(cores, seconds, args.steps, args.warmup)
+    sample = (f"{cores} clips x {seconds:.2f} s ({frames} frames each), one clip per host thread (OpenMP), "
+              f"float64 port of mel.FromMel GL-{GL_ITERS} incl. undomel; same per-frame work as the 10 s clips")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Go with un-vendored modules and no Go toolchain in the image: the CPU arm is the "
+                "line-by-line float64 C port in oracle/ (kind=port)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": f"configs[3]: batched FromMel Griffin-Lim {GL_ITERS} it, {CLIPS_PER_GPU} synthetic 10 s 44.1 kHz "
+                        f"clips per GPU (192 mels, Resolut 4096, Window 1280), sharded by clip, no collective",
+            "clips_per_gpu": CLIPS_PER_GPU, "frames_per_clip": 342, "gl_iters": GL_ITERS,
+            "distinct_spectrograms": BASE_CLIPS, "start_signal": "device U[0,1) per clip (seeded)",
+            "l2": "inputs larger than L2 (2.9 GB magnitudes + 1.8 GB signal per buffer)",
+            "parallelism": f"clip-sharded x{n_gpus}"}
+
+
+# ------------------------------------------------------------------------------- product arm
+def run_product(args):
+    rank, local_rank, world = dist_env()
+    n_gpus = args.gpus
+    use_dist = world > 1
+    if use_dist:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gomel_b200 import _lib
+    from util import synth_clip
+
+    ctx = _lib.Context(local_rank)
+    cfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
+    ctx.set_mel_tables(cfg, 0.0, 16000.0)
+    clips = args.clips
+    n = int(round(CLIP_SECONDS * SR))
+    npad, frames, ola = _lib.frames(cfg, n)
+    mel_per = frames * N_MELS * 2
+
+    # ---- synthetic spectrograms: BASE_CLIPS distinct clips -> GPU ToMel (the product path) -> tiled
+    nb = min(BASE_CLIPS, clips)
+    wav = np.stack([synth_clip(rank * 100000 + c, CLIP_SECONDS) for c in range(nb)]).astype(np.float32)
+    base_mel = np.empty((nb, mel_per), np.float32)
+    ctx.check(ctx.lib.gomel_to_mel_batch_host(ctx.h, C.byref(cfg), wav.ctypes.data_as(C.c_void_p), nb, n,
+                                              base_mel.ctypes.data_as(C.c_void_p), 16))
+    h_mel, h_mel_owner = ctx.pinned_array((clips, mel_per), np.float32)
+    for c in range(clips):
+        h_mel[c] = base_mel[c % nb]
+    h_out, h_out_owner = ctx.pinned_array((clips, ola), np.float32)
+    d_mel = ctx.dev_malloc(h_mel.nbytes)
+    d_out = ctx.dev_malloc(clips * ola * 4)
+    ctx.h2d(d_mel, h_mel)
+
+    def barrier():
+        ctx.sync()
+        if use_dist:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def step_device(seed):
+        ctx.check(ctx.lib.gomel_from_mel_dev(ctx.h, C.byref(cfg), d_mel, clips, frames, None, seed, ola, d_out))
+
+    def step_e2e(seed):
+        ctx.check(ctx.lib.gomel_from_mel_batch_host(ctx.h, C.byref(cfg), h_mel.ctypes.data_as(C.c_void_p), clips, frames,
+                                                    None, seed, h_out.ctypes.data_as(C.c_void_p), args.chunk))
+
+    # ---- device-resident timing
+    for w in range(args.warmup):
+        step_device(w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = ctx.launch_count()
+    hot_ms, hot_n = 0.0, 0
+    t_wall0 = time.time()
+    ctx.timer_start()
+    for s in range(args.steps):
+        step_device(1000 + s)
+        if args.per_kernel:
+            ms, nl = ctx.last_hot_kernel_ms()     # waits for this step's last Griffin-Lim launch
+            hot_ms += ms
+            hot_n += nl
+    dev_ms = ctx.timer_stop()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1)
+
+    # ---- end-to-end timing through the host-buffer C ABI call
+    for w in range(max(1, min(args.warmup, 2))):
+        step_e2e(w)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for s in range(args.steps):
+        step_e2e(2000 + s)
+    e2e_ms_dev = ctx.timer_stop()
+    ctx.sync()
+    e2e_ms = max((time.perf_counter() - t0) * 1e3, e2e_ms_dev)
+    barrier()
+    checksum = float(np.abs(h_out[:: max(1, clips // 8), ::4099]).sum())
+
+    if use_dist:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    audio_s_per_step = world * clips * frames * HOP / SR          # seconds of audio covered by the frames
+    value = audio_s_per_step * args.steps / (dev_ms / 1e3)
+    e2e_value = audio_s_per_step * args.steps / (e2e_ms / 1e3)
+    frame_iters = clips * frames * GL_ITERS
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        roofline = None
+        if hot_n:
+            per_launch_s = hot_ms / 1e3 / hot_n
+            achieved = BYTES_PER_FRAME_ITER * clips * frames / per_launch_s / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "gl_iter_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    tj = json.load(open(tp))
+                    traffic = tj["dram_bytes_per_frame_iter"] * clips * frames
+                except Exception:
+                    traffic = None
+            roofline = {"bound": "hbm", "kernel": "k_gl_iter<5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": BYTES_PER_FRAME_ITER * clips * frames,
+                        "avg_launch_ms": per_launch_s * 1e3, "launches_timed": hot_n,
+                        "kernel_share_of_step": hot_ms / dev_ms,
+                        "frame_iterations_per_s_per_gpu": frame_iters * args.steps / (hot_ms / 1e3)}
+        cpu = None
+        if world == 1:                              # rank 0 at N=1 only
+            if not args.no_cpu:
+                cores = os.cpu_count() or 1
+                secs = 10.0 if cores >= 4 else 5.0
+                v, fr, step_s = cpu_reference(cores, secs, 1, 0)
+                cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{cores} clips x {secs:.0f} s ({fr} frames), GL-{GL_ITERS}, one clip per host thread, "
+                                 f"{step_s:.1f} s wall; float64 C port of the Go path (no Go toolchain in the image)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_gpus),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_mel.nbytes),
+                    "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": e2e_ms / args.steps,
+                    "api": "gomel_from_mel_batch_host (pinned host float32 in/out, 3-stream pipeline)",
+                    "checksum": checksum},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "stft_frames_per_s": frame_iters * world * args.steps / (dev_ms / 1e3),
+            "stft_frames_per_s_note": "Griffin-Lim frame-iterations (one analysis STFT + one synthesis ISTFT each) per second, whole job",
+        }
+    if args.stft and rank == 0 and line is not None:
+        line["to_mel"] = bench_to_mel(ctx, cfg, _lib, args)
+    ctx.dev_free(d_mel)
+    ctx.dev_free(d_out)
+    ctx.host_free(h_mel_owner)
+    ctx.host_free(h_out_owner)
+    if rank == 0:
+        print(json.dumps(line))
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_to_mel(ctx, cfg, _lib, args):
+    """configs[1]: batched ToMel on 256 synthetic 10 s clips (STFT + mel projection only)."""
+    from util import synth_clip
+    clips = 256
+    n = int(round(CLIP_SECONDS * SR))
+    npad, frames, _ = _lib.frames(cfg, n)
+    stride = (npad + 3) & ~3
+    nb = 16
+    wav = np.zeros((clips, stride), np.float32)
+    base = np.stack([synth_clip(500 + c, CLIP_SECONDS) for c in range(nb)]).astype(np.float32)
+    for c in range(clips):
+        wav[c, :n] = base[c % nb]
+    d_sig = ctx.dev_malloc(wav.nbytes)
+    d_out = ctx.dev_malloc(clips * frames * N_MELS * 2 * 4)
+    ctx.h2d(d_sig, wav)
+    call = lambda: ctx.check(ctx.lib.gomel_to_mel_dev(ctx.h, C.byref(cfg), d_sig, clips, stride, npad, frames, d_out))
+    for _ in range(3):
+        call()
+    ctx.sync()
+    reps = 20
+    ctx.timer_start()
+    for _ in range(reps):
+        call()
+    ms = ctx.timer_stop() / reps
+    ctx.dev_free(d_sig)
+    ctx.dev_free(d_out)
+    peak, _ = peaks()
+    gbs = 6656 * clips * frames / (ms / 1e3) / 1e9
+    return {"workload": "configs[1]: ToMel, 256 x 10 s clips, device-resident", "frames_per_s": clips * frames / (ms / 1e3),
+            "ms": ms, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak,
+            "note": "87,552 frames = 0.58 GB algorithmic: smaller than L2 and FP32-bound, reported for completeness"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gomel_b200", choices=["gomel_b200", "reference"])
+    ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU (default: the named workload)")
+    ap.add_argument("--chunk", type=int, default=128, help="clips per pipeline chunk in the e2e call")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-stft", dest="stft", action="store_false", help="skip the ToMel side measurement")
+    ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")
+    args = ap.parse_args()
+    if args.impl != "reference":
+        args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -20,6 +20,8 @@ def synth_clip(c, seconds=10.0, sr=SR, n=None):
 
 
 def rel_l2(a, b):
-    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    if not (np.iscomplexobj(a) or np.iscomplexobj(b)):
+        a, b = a.astype(np.float64), b.astype(np.float64)
     d = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / d) if d > 0 else float(np.linalg.norm(a - b))
