@@ -273,7 +273,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
         p.sig_in = cur; p.sig_out = dst;
         p.hb_in = (i == 0) ? nullptr : (const float*)hb[(i - 1) & 1];
         p.hb_out = (float*)hb[i & 1];
-        k_gl_iter<kHS><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+        k_gl_iter<kHS><<<(unsigned)grid, kThreads, kGlSmemBytes, ctx->st>>>(p);
         ctx->launches++;
         cur = dst;
     }
@@ -387,7 +387,7 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_MEL>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_PHASE>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_SPEC>)) return rc;
-        if (int rc = set_smem_attr(ctx, k_gl_iter<kHS>)) return rc;
+        CU(cudaFuncSetAttribute(k_gl_iter<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
         if (int rc = set_smem_attr(ctx, k_istft_phase<kHS>)) return rc;
         return 0;
     };

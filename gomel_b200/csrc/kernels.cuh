@@ -14,11 +14,50 @@ namespace gomel {
 
 constexpr int kMagStride = 2052;     // floats per magnitude row: 2049 bins, 16-byte aligned rows
 
-// position of bin k inside a magnitude row: low byte nibble-swapped so that the digit-reversed
-// spectrum layout of fft4096_fwd reads rows with unit stride across a half-warp
+// position of bin k = k0 + 16*k1 + 256*k2 inside a magnitude row: k2*256 + rho(k0)*16 + k1 with
+// rho = rotate-left-by-1 of the 4-bit k0.  The digit-reversed spectrum layout of fft4096_fwd then
+// reads a row with unit stride across each half-warp (coalesced from HBM), and the two half-warps
+// of a warp (k0 and 16-k0, which differ in bit 3) land in different halves of the 32 smem banks.
 __host__ __device__ __forceinline__ int mag_pos(int k)
 {
-    return (k >= 2048) ? 2048 : ((k & ~255) | ((k & 15) << 4) | ((k >> 4) & 15));
+    if (k >= 2048) return 2048;
+    const int k0 = k & 15, k1 = (k >> 4) & 15;
+    const int rho = ((k0 & 7) << 1) | (k0 >> 3);
+    return (k & ~255) | (rho << 4) | k1;
+}
+// inverse of mag_pos for positions < 2048
+__host__ __device__ __forceinline__ int mag_unpos(int pos)
+{
+    const int rho = (pos >> 4) & 15, k1 = pos & 15;
+    const int k0 = (rho >> 1) | ((rho & 1) << 3);
+    return (pos & ~255) | (k1 << 4) | k0;
+}
+
+// ------------------------------------------------------------------ async bulk copy (TMA unit) helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar`.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
 }
 
 // ------------------------------------------------------------------ small conversion kernels
@@ -240,7 +279,8 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
         for (int i = threadIdx.x; i < 2 * n_mels; i += blockDim.x) e[i] = exp((double)m[i]);
         __syncthreads();
         float* out = mags + row * kMagStride;
-        for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes
+            const int i = mag_unpos(pos);
             const int lo = inv_lo[i], hi = inv_hi[i];
             const int nch = (i == 2047) ? 2 : 1;
             for (int l = 0; l < nch; l++) {
@@ -255,7 +295,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                     total /= (double)(hi - lo + 1);
                 }
                 const double v = fabs((total - tune_add) / tune_mul) * (1.0 / 4096.0);
-                out[l ? 2048 : mag_pos(i)] = (float)v;
+                out[l ? 2048 : pos] = (float)v;
             }
         }
     }
@@ -283,8 +323,9 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 {
     // cmplx.Rect(M, cmplx.Phase(X)) = M * X/|X|; Phase(0) = 0 -> (M, 0)   (mel/mel.go:98-102)
     const float n = fmaf(X.x, X.x, X.y * X.y);
-    if (n > 1e-30f) { const float r = M * rsqrtf(n); return make_float2(X.x * r, X.y * r); }
-    return make_float2(M, 0.0f);
+    const float r = M * rsqrtf(fmaxf(n, 1e-30f));
+    const bool ok = n > 1e-30f;
+    return make_float2(ok ? X.x * r : M, ok ? X.y * r : 0.0f);
 }
 
 // ------------------------------------------------------------------ K5: one Griffin-Lim iteration
@@ -295,11 +336,16 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 // Tile edges: samples whose contributing frames straddle two tiles are produced as two partial
 // sums -- the earlier tile's into sig_out (its tail), the later tile's into hb_out (its head) --
 // and summed on load (a+b is commutative, so both readers see the same value).
+constexpr int kGlMagBytes = 2 * kMagStride * 4;                 // two magnitude rows (frames A and B)
+constexpr int kGlSmemBytes = kSmemBytes + kGlMagBytes + 16;     // + one mbarrier
+
 template <int HS>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
+    float* const smag = reinterpret_cast<float*>(smem_raw + kSmemBytes);                 // [2][kMagStride]
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + kSmemBytes + kGlMagBytes);
     const Lanes L = make_lanes();
     load_tables(s, p.tables, L.t);
     constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
@@ -311,14 +357,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     const long sbase = (long)f0 * H;
     const float* __restrict__ sin_ = p.sig_in + (long)clip * p.tl.sig_stride + sbase;
     float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
-    const long lim = p.tl.sig_len - sbase;
+    const long lim_l = p.tl.sig_len - sbase;
+    const int lim = (int)(lim_l < 0x7fffff00L ? lim_l : 0x7fffff00L);     // tile-relative, fits int
     const bool has_prev = tile > 0, has_next = (tile + 1) < p.tl.n_tiles;
     const float* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)clip * p.tl.n_tiles + tile) * HALO : nullptr;
     const float* __restrict__ hin_next = hin_own ? hin_own + HALO : nullptr;
     float* __restrict__ hout = p.hb_out + ((long)clip * p.tl.n_tiles + tile) * HALO;
     const int t = L.t;
 
-    auto ld = [&](int row) -> float {          // row: sample offset inside the tile, multiple of 256
+    // generic (tile edge) load/store of one 256-sample row at tile-relative offset `row`
+    auto ld = [&](int row) -> float {
         const int o = row + t;
         float x = (o < lim) ? __ldg(sin_ + o) : 0.0f;
         if (hin_own) {
@@ -333,21 +381,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         if (has_prev && row < HALO) hout[o] = val;
         else sout[o] = val;
     };
+    // rows [row0, row0 + n*256) need no edge handling: inside the signal, outside both halo zones
+    auto plain_rows = [&](int row0, int n) -> bool {
+        const int end = row0 + n * 256;
+        return end <= lim && (!has_prev || row0 >= HALO) && (!(has_next && hin_own) || end <= tile_len);
+    };
 
-    float raw[NR], acc[NR];
+    if (t == 0) mbar_init(bar, 1);
+    float raw[NR], acc[NR], nxt[SH];
 #pragma unroll
     for (int j = 0; j < KEEP; j++) { raw[j] = ld(j * 256); acc[j] = 0.0f; }
+#pragma unroll
+    for (int j = 0; j < SH; j++) nxt[j] = ld((KEEP + j) * 256);
 
-    const int idx_lo = ((L.klow & 15) << 4) | (L.klow >> 4);
-    const int x256 = 256 - L.klow;
-    const int idx_hi = L.klow ? (((x256 & 15) << 4) | (x256 >> 4)) : 256;
+    const int idx_lo = mag_pos(L.klow);
+    const int idx_hi = L.klow ? mag_pos(256 - L.klow) : 256;
     const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
-    __syncthreads();
+    __syncthreads();                // tables + mbarrier init visible
 
     for (int pr = 0; pr < npairs; pr++) {
         const int off0 = pr * 2 * H;
+        const bool validB = (f0 + 2 * pr + 1) < p.tl.n_frames;
+        // stage this pair's target magnitudes with one TMA bulk copy; it lands during the forward FFT.
+        // (the buffer was last read in the previous pair's substitution stage, >= 2 barriers ago)
+        if (t == 0) {
+            const unsigned bytes = validB ? (unsigned)kGlMagBytes : (unsigned)(kMagStride * 4);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smag, mrow + (long)(2 * pr) * kMagStride, bytes, bar);
+        }
 #pragma unroll
-        for (int j = KEEP; j < NR; j++) { raw[j] = ld(off0 + j * 256); acc[j] = 0.0f; }
+        for (int j = 0; j < SH; j++) { raw[KEEP + j] = nxt[j]; acc[KEEP + j] = 0.0f; }
         float2 v[16];
 #pragma unroll
         for (int m = 0; m < 16; m++) { const float w = s.win[m * 256 + t]; v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
@@ -356,18 +419,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 
         fft4096_fwd(v, s, L);
 
+        // prefetch the next pair's new signal rows into registers; consumed at the top of the next pass
+        if (pr + 1 < npairs) {
+            const int r0 = off0 + 2 * H + KEEP * 256;
+            if (plain_rows(r0, SH)) {
+#pragma unroll
+                for (int j = 0; j < SH; j++) nxt[j] = __ldg(sin_ + r0 + j * 256 + t);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SH; j++) nxt[j] = ld(r0 + j * 256);
+            }
+        }
+
         // magnitude substitution on both frames at once.  With P = Z[N-k]:
         //   2*XA[k] = Z + conj P,  2*XB[k] = (Z - conj P)/i ; Y = M * X/|X| ; Z' = YA + i*YB
-        const bool validB = (f0 + 2 * pr + 1) < p.tl.n_frames;
-        const float* __restrict__ mA = mrow + (long)(2 * pr) * kMagStride;
-        const float* __restrict__ mB = mA + kMagStride;
+        mbar_wait(bar, (unsigned)(pr & 1));
         {
+            const float* __restrict__ mA = smag;
+            const float* __restrict__ mB = smag + kMagStride;
             float2 saved = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float mAlo = __ldg(mA + j * 256 + idx_lo), mAhi = __ldg(mA + j * 256 + idx_hi);
-                const float mBlo = validB ? __ldg(mB + j * 256 + idx_lo) : 0.0f;
-                const float mBhi = validB ? __ldg(mB + j * 256 + idx_hi) : 0.0f;
+                const float mAlo = mA[j * 256 + idx_lo], mAhi = mA[j * 256 + idx_hi];
+                const float mBlo = validB ? mB[j * 256 + idx_lo] : 0.0f;
+                const float mBhi = validB ? mB[j * 256 + idx_hi] : 0.0f;
                 float2 plo, phi;
                 if ((t >> 5) == 0) fetch_partner<true>(v, j, L, plo, phi, saved);
                 else               fetch_partner<false>(v, j, L, plo, phi, saved);
@@ -394,8 +469,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
             acc[m] = fmaf(v[m].x, w, acc[m]);
             acc[m + HS] = fmaf(v[m].y, w, acc[m + HS]);
         }
+        if (off0 + SH * 256 <= lim && (!has_prev || off0 >= HALO)) {
 #pragma unroll
-        for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
+            for (int j = 0; j < SH; j++) sout[off0 + j * 256 + t] = acc[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
+        }
 #pragma unroll
         for (int j = 0; j < KEEP; j++) acc[j] = acc[j + SH];
     }

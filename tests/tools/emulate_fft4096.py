@@ -80,7 +80,17 @@ def partner(v, L):
 
 
 def mag_pos(k):
-    return 2048 if k >= 2048 else ((k & ~255) | ((k & 15) << 4) | ((k >> 4) & 15))
+    if k >= 2048:
+        return 2048
+    k0, k1 = k & 15, (k >> 4) & 15
+    rho = ((k0 & 7) << 1) | (k0 >> 3)
+    return (k & ~255) | (rho << 4) | k1
+
+
+def mag_unpos(pos):
+    rho, k1 = (pos >> 4) & 15, pos & 15
+    k0 = (rho >> 1) | ((rho & 1) << 3)
+    return (pos & ~255) | (k1 << 4) | k0
 
 
 def main():
@@ -103,9 +113,14 @@ def main():
     assert np.abs(back - v).max() < 1e-12
     # magnitude row indices used by k_gl_iter
     klow = L['klow']
-    idx_lo = ((klow & 15) << 4) | (klow >> 4)
-    x256 = 256 - klow
-    idx_hi = np.where(klow != 0, ((x256 & 15) << 4) | (x256 >> 4), 256)
+    idx_lo = np.array([mag_pos(int(k)) for k in klow])
+    idx_hi = np.array([mag_pos(256 - int(k)) if k else 256 for k in klow])
+    assert all(mag_unpos(mag_pos(k)) == k for k in range(2048))
+    # staged rows are read conflict-free: 32 lanes of a warp hit 32 distinct banks (one duplicate allowed in warp 0)
+    for w in range(8):
+        for idx in (idx_lo, idx_hi):
+            banks = idx[w * 32:(w + 1) * 32] % 32
+            assert len(set(banks.tolist())) >= 31, (w, sorted(banks.tolist()))
     for t in range(256):
         for j in range(8):
             kk = klow[t] + 256 * j
