@@ -1,0 +1,177 @@
+// Package gomelcuda is the thin cgo layer over libgomelcuda.so (include/gomel_cuda.h).
+// NOT COMPILED IN THE BUILD IMAGE (no Go toolchain there) -- written against the C header by
+// inspection; see INTEGRATION.md.  One cgo crossing per API call, never per frame.
+package gomelcuda
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../gomel_b200 -lgomelcuda -Wl,-rpath,${SRCDIR}/../../../gomel_b200
+#include <stdlib.h>
+#include "gomel_cuda.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"math"
+	"sync"
+	"unsafe"
+)
+
+// Config mirrors gomel_config.
+type Config struct {
+	NFFT, Hop, NMels, NFreqs, GLIters int
+	TuneMul, TuneAdd, VolumeBoost     float64
+}
+
+func (c Config) c() C.gomel_config {
+	return C.gomel_config{n_fft: C.int(c.NFFT), hop: C.int(c.Hop), n_mels: C.int(c.NMels), n_freqs: C.int(c.NFreqs),
+		gl_iters: C.int(c.GLIters), tune_mul: C.double(c.TuneMul), tune_add: C.double(c.TuneAdd),
+		volume_boost: C.double(c.VolumeBoost)}
+}
+
+// Ctx owns one gomel_ctx.  Methods are safe for concurrent use (the library serialises per context);
+// use one Ctx per goroutine pool slot for concurrency.
+type Ctx struct {
+	h         *C.gomel_ctx
+	tablesKey [4]float64
+}
+
+var (
+	defOnce sync.Once
+	defCtx  *Ctx
+	defErr  error
+)
+
+// Default returns the process-wide context on device 0.  There is no CPU fallback: without a GPU
+// this returns an error and every transform fails.
+func Default() (*Ctx, error) {
+	defOnce.Do(func() { defCtx, defErr = New(0) })
+	return defCtx, defErr
+}
+
+func New(device int) (*Ctx, error) {
+	var h *C.gomel_ctx
+	if rc := C.gomel_ctx_create(C.int(device), &h); rc != 0 {
+		return nil, fmt.Errorf("gomel_ctx_create: %d (no CUDA device?)", int(rc))
+	}
+	return &Ctx{h: h}, nil
+}
+
+func (x *Ctx) Close() { C.gomel_ctx_destroy(x.h); x.h = nil }
+
+func (x *Ctx) err(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return errors.New(C.GoString(C.gomel_last_error(x.h)))
+}
+
+// Frames = pad (mel/impl.go:429-455) + gossp NumFrames + ISTFT length.
+func Frames(cfg Config, n int) (padded, frames, ola int, err error) {
+	cc := cfg.c()
+	var a, b, c C.long
+	if rc := C.gomel_frames(&cc, C.long(n), &a, &b, &c); rc != 0 {
+		return 0, 0, 0, errors.New("gomel_frames: bad length")
+	}
+	return int(a), int(b), int(c), nil
+}
+
+func hzToMel(v float64) float64 { return 1127.0 * math.Log(1.0+(v/700.0)) }   // mel/impl.go:304-308
+func melToHz(v float64) float64 { return 700.0 * (math.Exp(v/1127.0) - 1.0) } // mel/impl.go:298-302
+
+// SetMelTables computes the (int(inlo), int(inhi), modlo) triples of domel / undomel with Go's own
+// math.Exp / math.Log -- exactly the expressions of mel/impl.go:313-323 and :350-360 -- and hands
+// them to the library, so the two 1-ulp-fragile band edges fall where the reference puts them.
+func (x *Ctx) SetMelTables(cfg Config, fmin, fmax float64) error {
+	key := [4]float64{float64(cfg.NFFT), float64(cfg.NMels), fmin, fmax}
+	if x.tablesKey == key {
+		return nil
+	}
+	fs, mels := cfg.NFFT/2, cfg.NMels
+	flo, fhi, fmod := make([]C.int, mels), make([]C.int, mels), make([]C.double, mels)
+	melbin := hzToMel(fmax) / float64(mels)
+	for i := 0; i < mels; i++ {
+		vallo := float64(fs) * (fmin + melToHz(melbin*float64(i))) / (fmax + fmin)
+		valhi := float64(fs) * (fmin + melToHz(melbin*float64(i+1))) / (fmax + fmin)
+		inlo, modlo := math.Modf(vallo)
+		inhi := math.Floor(valhi)
+		if inlo < 0 {
+			inlo, modlo, inhi = 0, 0, 0
+		}
+		flo[i], fhi[i], fmod[i] = C.int(int(inlo)), C.int(int(inhi)), C.double(modlo)
+	}
+	ilo, ihi, imod := make([]C.int, fs), make([]C.int, fs), make([]C.double, fs)
+	filterbin := hzToMel(fmax) / float64(mels)
+	for i := 0; i < fs; i++ {
+		vallo := hzToMel((float64(i)*(fmax+fmin)/float64(fs))-fmin) / filterbin
+		valhi := hzToMel((float64(i+1)*(fmax+fmin)/float64(fs))-fmin) / filterbin
+		inlo, modlo := math.Modf(vallo)
+		inhi := math.Floor(valhi)
+		if inlo < 0 {
+			inlo, modlo, inhi = 0, 0, 0
+		}
+		ilo[i], ihi[i], imod[i] = C.int(int(inlo)), C.int(int(inhi)), C.double(modlo)
+	}
+	cc := cfg.c()
+	if e := x.err(C.gomel_set_mel_tables(x.h, &cc, &flo[0], &fhi[0], &fmod[0], &ilo[0], &ihi[0], &imod[0])); e != nil {
+		return e
+	}
+	x.tablesKey = key
+	return nil
+}
+
+// ToMel: [][2]float64 is a contiguous double[2n], passed as &out[0] (no Go pointer to Go pointer).
+func (x *Ctx) ToMel(cfg Config, wav []float64) ([][2]float64, error) {
+	_, frames, _, err := Frames(cfg, len(wav))
+	if err != nil {
+		return nil, err
+	}
+	out := make([][2]float64, frames*cfg.NMels)
+	cc := cfg.c()
+	rc := C.gomel_to_mel(x.h, &cc, (*C.double)(unsafe.Pointer(&wav[0])), C.long(len(wav)),
+		(*C.double)(unsafe.Pointer(&out[0])))
+	return out, x.err(rc)
+}
+
+func (x *Ctx) FromMel(cfg Config, mel [][2]float64, init []float64) ([]float64, error) {
+	frames := len(mel) / cfg.NMels
+	out := make([]float64, cfg.NFFT+(frames-1)*cfg.Hop)
+	cc := cfg.c()
+	var ip *C.double
+	if len(init) > 0 {
+		ip = (*C.double)(unsafe.Pointer(&init[0]))
+	}
+	rc := C.gomel_from_mel(x.h, &cc, (*C.double)(unsafe.Pointer(&mel[0])), C.long(frames), ip, 0,
+		(*C.double)(unsafe.Pointer(&out[0])))
+	return out, x.err(rc)
+}
+
+func (x *Ctx) ToPhase(cfg Config, wav []float64) ([][2]float64, error) {
+	_, frames, _, err := Frames(cfg, len(wav))
+	if err != nil {
+		return nil, err
+	}
+	out := make([][2]float64, frames*cfg.NFreqs)
+	cc := cfg.c()
+	rc := C.gomel_to_phase(x.h, &cc, (*C.double)(unsafe.Pointer(&wav[0])), C.long(len(wav)),
+		(*C.double)(unsafe.Pointer(&out[0])))
+	return out, x.err(rc)
+}
+
+func (x *Ctx) FromPhase(cfg Config, spec [][2]float64) ([]float64, error) {
+	frames := len(spec) / cfg.NFreqs
+	out := make([]float64, cfg.NFFT+(frames-1)*cfg.Hop)
+	cc := cfg.c()
+	rc := C.gomel_from_phase(x.h, &cc, (*C.double)(unsafe.Pointer(&spec[0])), C.long(frames),
+		(*C.double)(unsafe.Pointer(&out[0])))
+	return out, x.err(rc)
+}
+
+func (x *Ctx) Image(buf [][2]float64, mels int) ([]uint16, error) {
+	out := make([]uint16, (len(buf)/mels)*mels)
+	rc := C.gomel_image(x.h, (*C.double)(unsafe.Pointer(&buf[0])), C.long(len(buf)), C.int(mels),
+		(*C.ushort)(unsafe.Pointer(&out[0])), nil)
+	return out, x.err(rc)
+}
