@@ -68,6 +68,17 @@ SIGNATURES = {
     "gomel_stft_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, C.c_long, C.c_long, _vp]),
     "gomel_from_mel_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, C.c_long, _vp]),
     "gomel_from_phase_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, C.c_long, _vp]),
+    "gomel_ts_create": (C.c_int, [_vp, _cp, C.c_long, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "gomel_ts_destroy": (None, [_vp]),
+    "gomel_ts_range": (C.c_int, [_vp, _lp, _lp, _lp, _lp]),
+    "gomel_ts_load": (C.c_int, [_vp, _vp, _vp, C.c_ulonglong]),
+    "gomel_ts_iterate": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "gomel_ts_halo_ptrs": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "gomel_ts_comm_stream": (_vp, [_vp]),
+    "gomel_ts_comm_begin": (C.c_int, [_vp, C.c_int]),
+    "gomel_ts_comm_end": (C.c_int, [_vp, C.c_int]),
+    "gomel_ts_finish": (C.c_int, [_vp, C.c_int, _vp]),
+    "gomel_copy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "gomel_from_mel_batch_host": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, _vp, C.c_int]),
     "gomel_to_mel_batch_host": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_int]),
 }

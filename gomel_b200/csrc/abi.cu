@@ -261,7 +261,8 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
     p.mags = d_mags;
     void *tmp = nullptr, *hb[2] = { nullptr, nullptr };
     if (iters > 1) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &tmp)) return rc; }
-    const size_t hb_bytes = (size_t)n_clips * p.tl.n_tiles * kHalo * 4 + 16;
+    p.hb_tiles = p.tl.n_tiles + 1; p.tile_lo = 0; p.tiles_in_launch = p.tl.n_tiles;
+    const size_t hb_bytes = (size_t)n_clips * p.hb_tiles * kHalo * 4 + 16;
     if (int rc = ensure(ctx, S_HB0, hb_bytes, &hb[0])) return rc;
     if (int rc = ensure(ctx, S_HB1, hb_bytes, &hb[1])) return rc;
     const long grid = (long)n_clips * p.tl.n_tiles;
@@ -282,7 +283,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
     if (p.tl.n_tiles > 1) {
         const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;
         k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, kHop, kHalo,
-                                                           n_clips, 0, p);
+                                                           n_clips, 0, 1, p.hb_tiles, p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -332,7 +333,8 @@ int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_
     p.gain_head = ctx->d_gain_head; p.gain_mid = ctx->d_gain_mid; p.gain_tail = ctx->d_gain_tail;
     p.head_len = ctx->gain_head_len; p.tail_len = ctx->gain_tail_len;
     void* hb;
-    if (int rc = ensure(ctx, S_HB0, (size_t)n_clips * p.tl.n_tiles * kHalo * 4 + 16, &hb)) return rc;
+    p.hb_tiles = p.tl.n_tiles + 1; p.tile_lo = 0; p.tiles_in_launch = p.tl.n_tiles;
+    if (int rc = ensure(ctx, S_HB0, (size_t)n_clips * p.hb_tiles * kHalo * 4 + 16, &hb)) return rc;
     p.hb_out = (float*)hb;
     const long grid = (long)n_clips * p.tl.n_tiles;
     if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
@@ -340,7 +342,8 @@ int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_
     ctx->launches++;
     if (p.tl.n_tiles > 1) {
         const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;
-        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb, p.tl, kHop, kHalo, n_clips, 1, p);
+        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb, p.tl, kHop, kHalo, n_clips, 1, 1,
+                                                           p.hb_tiles, p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -864,6 +867,225 @@ int gomel_to_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float
     for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); }
     if (rc) return rc;
     CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------- time-split Griffin-Lim (config 5)
+struct gomel_ts {
+    gomel_ctx* ctx = nullptr;
+    gomel_config cfg;
+    int rank = 0, world = 1;
+    long f_begin = 0, n_local = 0, sample_begin = 0, n_samples = 0;
+    Tiling tl;
+    int ext_prev = 0, ext_next = 0;
+    float *sig[2] = { nullptr, nullptr }, *hb[2] = { nullptr, nullptr }, *mags = nullptr;
+    cudaStream_t st_edge = nullptr, st_comm = nullptr;
+    cudaEvent_t ev_edge = nullptr, ev_int = nullptr, ev_comm = nullptr;
+    bool have_edge = false, have_int = false, have_comm = false;
+};
+
+extern "C" {
+
+int gomel_ts_create(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_total, int rank, int world,
+                    int tile_frames, gomel_ts** out)
+{
+    if (!ctx || !out) return GOMEL_E_ARG;
+    Guard g(ctx);
+    *out = nullptr;
+    if (int rc = check_cfg(ctx, cfg)) return rc;
+    if (world < 1 || rank < 0 || rank >= world || n_frames_total <= 0) return fail(ctx, GOMEL_E_ARG, "bad rank/world/frames");
+    int T = tile_frames > 0 ? tile_frames : 16;
+    if (T & 1) T++;
+    if (T < 4) T = 4;
+    const long tiles_total = (n_frames_total + T - 1) / T;
+    if (tiles_total < world) return fail(ctx, GOMEL_E_ARG, "fewer tiles than ranks: lower tile_frames");
+    const long a = rank * tiles_total / world, b = (rank + 1) * tiles_total / world;
+    gomel_ts* ts = new gomel_ts();
+    ts->ctx = ctx; ts->cfg = *cfg; ts->rank = rank; ts->world = world;
+    ts->f_begin = a * T;
+    const long f_end = (b * T < n_frames_total) ? b * T : n_frames_total;
+    ts->n_local = f_end - ts->f_begin;
+    ts->sample_begin = ts->f_begin * kHop;
+    ts->n_samples = ts->n_local * kHop + kHalo;
+    ts->ext_prev = rank > 0; ts->ext_next = rank + 1 < world;
+    ts->tl.n_frames = (int)ts->n_local; ts->tl.tile_frames = T; ts->tl.n_tiles = (int)((ts->n_local + T - 1) / T);
+    ts->tl.sig_stride = ts->n_samples; ts->tl.sig_len = ts->n_samples;
+    auto boot = [&]() -> int {
+        const size_t hb_bytes = (size_t)(ts->tl.n_tiles + 1) * kHalo * 4;
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc(&ts->sig[i], (size_t)ts->n_samples * 4));
+            CU(cudaMalloc(&ts->hb[i], hb_bytes));
+            CU(cudaMemsetAsync(ts->hb[i], 0, hb_bytes, ctx->st));
+        }
+        CU(cudaMalloc(&ts->mags, (size_t)ts->n_local * kMagStride * 4));
+        CU(cudaStreamCreateWithFlags(&ts->st_edge, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ts->st_comm, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ts->ev_edge, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ts->ev_int, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ts->ev_comm, cudaEventDisableTiming));
+        return 0;
+    };
+    if (int rc = boot()) { gomel_ts_destroy(ts); return rc; }
+    *out = ts;
+    return 0;
+}
+
+void gomel_ts_destroy(gomel_ts* ts)
+{
+    if (!ts) return;
+    cudaSetDevice(ts->ctx->device);
+    cudaStreamSynchronize(ts->ctx->st);
+    if (ts->st_edge) cudaStreamSynchronize(ts->st_edge);
+    if (ts->st_comm) cudaStreamSynchronize(ts->st_comm);
+    for (int i = 0; i < 2; i++) { cudaFree(ts->sig[i]); cudaFree(ts->hb[i]); }
+    cudaFree(ts->mags);
+    if (ts->ev_edge) cudaEventDestroy(ts->ev_edge);
+    if (ts->ev_int) cudaEventDestroy(ts->ev_int);
+    if (ts->ev_comm) cudaEventDestroy(ts->ev_comm);
+    if (ts->st_edge) cudaStreamDestroy(ts->st_edge);
+    if (ts->st_comm) cudaStreamDestroy(ts->st_comm);
+    delete ts;
+}
+
+int gomel_ts_range(gomel_ts* ts, long* frame_begin, long* n_frames_local, long* sample_begin, long* n_samples_local)
+{
+    if (!ts) return GOMEL_E_ARG;
+    if (frame_begin) *frame_begin = ts->f_begin;
+    if (n_frames_local) *n_frames_local = ts->n_local;
+    if (sample_begin) *sample_begin = ts->sample_begin;
+    if (n_samples_local) *n_samples_local = ts->n_samples;
+    return 0;
+}
+
+int gomel_ts_load(gomel_ts* ts, const float* d_mel_local, const float* d_init_local, unsigned long long seed)
+{
+    if (!ts || !d_mel_local) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    if (int rc = mags_dev<float>(ctx, &ts->cfg, d_mel_local, ts->n_local, ts->mags)) return rc;
+    if (d_init_local) CU(cudaMemcpyAsync(ts->sig[0], d_init_local, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    else {
+        k_fill_uniform<<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(ts->sig[0], ts->n_samples, seed, ts->sample_begin);
+        ctx->launches++;
+    }
+    ts->have_edge = ts->have_int = ts->have_comm = false;
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int gomel_ts_iterate(gomel_ts* ts, int iter, int part)
+{
+    if (!ts || iter < 0 || part < 0 || part > 2) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    SynParams p = {};
+    p.tables = ctx->d_tables; p.tl = ts->tl; p.mags = ts->mags;
+    p.sig_in = ts->sig[iter & 1]; p.sig_out = ts->sig[(iter + 1) & 1];
+    p.hb_in = iter ? ts->hb[(iter + 1) & 1] : nullptr; p.hb_out = ts->hb[iter & 1];
+    p.hb_tiles = ts->tl.n_tiles + 1; p.ext_prev = ts->ext_prev; p.ext_next = ts->ext_next;
+    const int nt = ts->tl.n_tiles;
+    // boundary tiles: tile 0 if a previous rank exists, tile nt-1 if a next rank exists
+    int edges[2], n_edge = 0;
+    if (ts->ext_prev) edges[n_edge++] = 0;
+    if (ts->ext_next && !(n_edge && nt == 1)) edges[n_edge++] = nt - 1;
+    const int lo = ts->ext_prev ? 1 : 0, hi = ts->ext_next ? nt - 1 : nt;      // interior [lo, hi)
+    if (part == 0) {
+        if (ts->have_comm) CU(cudaStreamWaitEvent(ctx->st, ts->ev_comm, 0));
+        if (ts->have_edge) CU(cudaStreamWaitEvent(ctx->st, ts->ev_edge, 0));
+        p.tile_lo = 0; p.tiles_in_launch = nt;
+        k_gl_iter<kHS><<<nt, kThreads, kGlSmemBytes, ctx->st>>>(p);
+        ctx->launches++;
+        CU(cudaEventRecord(ts->ev_edge, ctx->st)); ts->have_edge = true;
+        CU(cudaEventRecord(ts->ev_int, ctx->st)); ts->have_int = true;
+    } else if (part == 1) {
+        if (ts->have_int) CU(cudaStreamWaitEvent(ts->st_edge, ts->ev_int, 0));
+        if (ts->have_comm) CU(cudaStreamWaitEvent(ts->st_edge, ts->ev_comm, 0));
+        if (n_edge > 0) {
+            p.edge_mode = 1; p.edge_tile0 = edges[0]; p.edge_tile1 = edges[n_edge - 1];
+            k_gl_iter<kHS><<<n_edge, kThreads, kGlSmemBytes, ts->st_edge>>>(p);
+            ctx->launches++;
+        }
+        CU(cudaEventRecord(ts->ev_edge, ts->st_edge)); ts->have_edge = true;
+    } else {
+        // interior of iteration `iter` needs the boundary tiles of iteration iter-1 (recorded before
+        // this iteration's part-1 call re-records ev_edge; callers issue part 2 of iteration i-1
+        // before part 1 of iteration i, so the wait below is enqueued by the previous part-1 call)
+        if (hi > lo) {
+            p.tile_lo = lo; p.tiles_in_launch = hi - lo;
+            k_gl_iter<kHS><<<hi - lo, kThreads, kGlSmemBytes, ctx->st>>>(p);
+            ctx->launches++;
+        }
+        CU(cudaEventRecord(ts->ev_int, ctx->st)); ts->have_int = true;
+        // the NEXT iteration's interior must not start before this iteration's boundary tiles finished
+        if (ts->have_edge) CU(cudaStreamWaitEvent(ctx->st, ts->ev_edge, 0));
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int gomel_ts_halo_ptrs(gomel_ts* ts, int iter, float** send_tail, float** send_head, float** recv_tail, float** recv_head)
+{
+    if (!ts || iter < 0) return GOMEL_E_ARG;
+    float* out = ts->sig[(iter + 1) & 1];
+    float* hbo = ts->hb[iter & 1];
+    if (send_tail) *send_tail = ts->ext_next ? out + ts->n_local * kHop : nullptr;
+    if (recv_head) *recv_head = ts->ext_next ? hbo + (long)ts->tl.n_tiles * kHalo : nullptr;
+    if (send_head) *send_head = ts->ext_prev ? hbo : nullptr;
+    if (recv_tail) *recv_tail = ts->ext_prev ? out : nullptr;
+    return 0;
+}
+
+void* gomel_ts_comm_stream(gomel_ts* ts) { return ts ? (void*)ts->st_comm : nullptr; }
+
+int gomel_ts_comm_begin(gomel_ts* ts, int iter)
+{
+    (void)iter;
+    if (!ts) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    if (ts->have_edge) CU(cudaStreamWaitEvent(ts->st_comm, ts->ev_edge, 0));
+    return 0;
+}
+
+int gomel_ts_comm_end(gomel_ts* ts, int iter)
+{
+    (void)iter;
+    if (!ts) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    CU(cudaEventRecord(ts->ev_comm, ts->st_comm)); ts->have_comm = true;
+    return 0;
+}
+
+int gomel_ts_finish(gomel_ts* ts, int iters, float* d_out_local)
+{
+    if (!ts || !d_out_local || iters < 0) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    CU(cudaStreamSynchronize(ts->st_edge));
+    CU(cudaStreamSynchronize(ts->st_comm));
+    CU(cudaStreamSynchronize(ctx->st));
+    float* fin = ts->sig[iters & 1];
+    const int t_first = ts->ext_prev ? 0 : 1;
+    if (iters > 0 && ts->tl.n_tiles - t_first > 0) {
+        SynParams p = {};
+        const long total = (long)(ts->tl.n_tiles - t_first) * kHalo;
+        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(fin, ts->hb[(iters - 1) & 1], ts->tl, kHop, kHalo, 1, 0, t_first,
+                                                           ts->tl.n_tiles + 1, p);
+        ctx->launches++;
+    }
+    CU(cudaMemcpyAsync(d_out_local, fin, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int gomel_copy_d2d(gomel_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : ctx->st));
     return 0;
 }
 

@@ -81,12 +81,12 @@ __global__ void k_fill_f32(float* __restrict__ out, long n, float v)
 }
 // counter-based U[0,1) fill for the Griffin-Lim start signal when the caller injects none
 // (mel/mel.go:80-83 draws rand.Float64(); same distribution, not bit-compatible with math/rand)
-__global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long long seed)
+__global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long long seed, long index_offset = 0)
 {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long step = (long)gridDim.x * blockDim.x;
     for (; i < n; i += step) {
-        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + index_offset + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
@@ -317,6 +317,11 @@ struct SynParams {
     int n_freqs;
     const float* gain_head; const float* gain_mid; const float* gain_tail;   // window-sum normalisation
     int head_len, tail_len;
+    // launch subset + time-split neighbours (config 5): defaults 0 = whole clip on this GPU
+    int hb_tiles;            // tiles per clip in hb buffers (n_tiles + 1: last slot = head partial of the next rank)
+    int tile_lo, tiles_in_launch;     // this launch covers tiles [tile_lo, tile_lo + tiles_in_launch)
+    int edge_mode, edge_tile0, edge_tile1;   // edge_mode: grid = 1 or 2 CTAs mapped to these tiles
+    int ext_prev, ext_next;  // a previous / next rank continues the clip beyond this buffer
 };
 
 __device__ __forceinline__ float2 subst_phase(float2 X, float M)
@@ -349,7 +354,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     const Lanes L = make_lanes();
     load_tables(s, p.tables, L.t);
     constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
-    const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
+    int tile, clip;
+    if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
+    else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = blockIdx.x / p.tiles_in_launch; }
     const int f0 = tile * p.tl.tile_frames;
     const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
     const int npairs = (nf + 1) >> 1;
@@ -359,10 +366,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
     const long lim_l = p.tl.sig_len - sbase;
     const int lim = (int)(lim_l < 0x7fffff00L ? lim_l : 0x7fffff00L);     // tile-relative, fits int
-    const bool has_prev = tile > 0, has_next = (tile + 1) < p.tl.n_tiles;
-    const float* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)clip * p.tl.n_tiles + tile) * HALO : nullptr;
+    const bool has_prev = tile > 0 || p.ext_prev, has_next = (tile + 1) < p.tl.n_tiles || p.ext_next;
+    const float* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)clip * p.hb_tiles + tile) * HALO : nullptr;
     const float* __restrict__ hin_next = hin_own ? hin_own + HALO : nullptr;
-    float* __restrict__ hout = p.hb_out + ((long)clip * p.tl.n_tiles + tile) * HALO;
+    float* __restrict__ hout = p.hb_out + ((long)clip * p.hb_tiles + tile) * HALO;
     const int t = L.t;
 
     // generic (tile edge) load/store of one 256-sample row at tile-relative offset `row`
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
     const long lim = p.tl.sig_len - sbase;
     const bool has_prev = tile > 0, has_next = (tile + 1) < p.tl.n_tiles;
-    float* __restrict__ hout = p.hb_out + ((long)clip * p.tl.n_tiles + tile) * HALO;
+    float* __restrict__ hout = p.hb_out + ((long)clip * p.hb_tiles + tile) * HALO;
     const int t = L.t, nfq = p.n_freqs;
 
     auto st = [&](int row, float val) {
@@ -585,22 +592,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     for (int j = 0; j < KEEP; j++) st(npairs * 2 * H + j * 256, acc[j]);
 }
 
-// finishes the samples shared by two tiles: sig[s] = (sig[s] + hb[s]) * gain
+// finishes the samples shared by two tiles: sig[s] = (sig[s] + hb[s]) * gain, for the head regions of
+// tiles t_first .. n_tiles-1 (t_first = 0 when a previous rank's tail partial sits in sig[0..halo))
 __global__ void k_halo_fix(float* __restrict__ sig, const float* __restrict__ hb, Tiling tl, int hop, int halo,
-                           int n_clips, int use_gain, SynParams gp)
+                           int n_clips, int use_gain, int t_first, int hb_tiles, SynParams gp)
 {
-    const long per_clip = (long)(tl.n_tiles - 1) * halo;
+    const long per_clip = (long)(tl.n_tiles - t_first) * halo;
     const long total = per_clip * n_clips;
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long step = (long)gridDim.x * blockDim.x;
     for (; i < total; i += step) {
         const int clip = (int)(i / per_clip);
         const long r = i - (long)clip * per_clip;
-        const int tile = (int)(r / halo) + 1, o = (int)(r % halo);
+        const int tile = (int)(r / halo) + t_first, o = (int)(r % halo);
         const long s_abs = (long)tile * tl.tile_frames * hop + o;
         if (s_abs >= tl.sig_len) continue;
         float* d = sig + (long)clip * tl.sig_stride + s_abs;
-        float x = *d + hb[((long)clip * tl.n_tiles + tile) * halo + o];
+        float x = *d + hb[((long)clip * hb_tiles + tile) * halo + o];
         if (use_gain) x *= gain_at(gp, s_abs, hop);
         *d = x;
     }

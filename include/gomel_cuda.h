@@ -143,6 +143,36 @@ int  gomel_from_mel_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_
 int  gomel_from_phase_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *d_spec, int n_clips,
                           long n_frames, long sig_stride, float *d_out);
 
+/* ---- one long clip split by time across ranks (config 5) -------------------------------------
+ * Rank `rank` of `world` owns a contiguous, tile-aligned range of the clip's frames and keeps its
+ * part of the signal and of the target magnitudes resident for all Griffin-Lim iterations.  Per
+ * iteration and per rank boundary exactly two partial sums of Resolut-Window = 2816 floats cross:
+ * the earlier rank's TAIL partial (-> next rank) and the later rank's HEAD partial (-> previous
+ * rank); each side adds local + received (a+b == b+a, so both hold identical samples).
+ * The library does not call NCCL itself: it exposes the four device pointers and a communication
+ * stream, and orders that stream against its kernels with events; the caller issues the
+ * send/recv pair (torch.distributed NCCL in gomel_b200/timesplit.py) on that stream.
+ *   part: 0 = all tiles in one launch; 1 = only the tiles that touch a rank boundary (own stream);
+ *         2 = the interior tiles -- lets the exchange of iteration i overlap its interior work. */
+typedef struct gomel_ts gomel_ts;
+int  gomel_ts_create(gomel_ctx *ctx, const gomel_config *cfg, long n_frames_total, int rank, int world,
+                     int tile_frames, gomel_ts **out);
+void gomel_ts_destroy(gomel_ts *ts);
+/* frames [frame_begin, frame_begin+n_frames_local); local buffers hold global samples
+ * [sample_begin, sample_begin+n_samples_local), n_samples_local = n_frames_local*Window + 2816 */
+int  gomel_ts_range(gomel_ts *ts, long *frame_begin, long *n_frames_local, long *sample_begin, long *n_samples_local);
+/* d_mel_local: [n_frames_local][n_mels][2] float32; d_init_local: n_samples_local floats or NULL
+ * (device U[0,1) keyed by the GLOBAL sample index, so the result does not depend on the split) */
+int  gomel_ts_load(gomel_ts *ts, const float *d_mel_local, const float *d_init_local, unsigned long long seed);
+int  gomel_ts_iterate(gomel_ts *ts, int iter, int part);
+int  gomel_ts_halo_ptrs(gomel_ts *ts, int iter, float **send_tail, float **send_head, float **recv_tail, float **recv_head);
+void *gomel_ts_comm_stream(gomel_ts *ts);                 /* cudaStream_t */
+int  gomel_ts_comm_begin(gomel_ts *ts, int iter);          /* comm stream waits for iteration iter's boundary tiles */
+int  gomel_ts_comm_end(gomel_ts *ts, int iter);            /* marks the exchange of iteration iter done */
+/* folds the last partials in and copies the local signal (n_samples_local floats) to d_out_local */
+int  gomel_ts_finish(gomel_ts *ts, int iters, float *d_out_local);
+int  gomel_copy_d2d(gomel_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream /* NULL = ctx stream */);
+
 /* ---- pipelined host batch (end-to-end: pinned host float32 in, float32 out, H2D/compute/D2H
  * overlapped chunk by chunk on three streams).  mel: [n_clips][n_frames*n_mels*2],
  * init: [n_clips][ola_len] or NULL, out: [n_clips][ola_len]. */

@@ -302,3 +302,26 @@ def test_launch_counter_counts_kernels(mctx, lib, oracle):
     from gomel_b200 import Phase
     Phase(num_freqs=768).to_phase(synth_clip(1, 0.2))
     assert mctx.launch_count() > before
+
+
+# ------------------------------------------------------------------ time-split (config 5) on one GPU
+@pytest.mark.parametrize("world,overlap,seconds,iters", [(2, False, 2.0, 3), (3, True, 2.0, 4), (4, True, 3.1, 2)])
+def test_timesplit_emulated_ranks_match_single_gpu(mctx, lib, oracle, world, overlap, seconds, iters):
+    """world ranks emulated as sessions of one process: boundary partials exchanged by D2D copies.
+    With the same tile size the partial sums are identical -> bit-identical to the unsplit run."""
+    from gomel_b200 import timesplit
+    cfg = mel_cfg(lib, iters=iters)
+    wav = synth_clip(50, seconds)
+    mel = oracle.to_mel(oracle.config(), wav)
+    frames = len(mel) // 192
+    ola = 4096 + (frames - 1) * 1280
+    init = np.random.default_rng(77).random(ola)
+    split = timesplit.run_local(mctx, cfg, mel, init.astype(np.float32), iters, world, tile_frames=8, overlap=overlap)
+    mctx.set_tile_frames(8)
+    mel32 = mel.astype(np.float32).astype(np.float64)          # the split path takes float32 spectrograms
+    whole = mctx.from_mel(cfg, mel32, init=init.astype(np.float32).astype(np.float64))
+    mctx.set_tile_frames(0)
+    assert split.shape == (ola,)
+    assert np.array_equal(split.astype(np.float64), whole)
+    ref = oracle.from_mel(oracle.config(gl_iters=iters), mel, init.astype(np.float32).astype(np.float64))
+    assert rel_l2(split, ref) < TOL_GL
