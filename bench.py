@@ -316,6 +316,93 @@ def run_product(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------- config 5 side bench
+def run_timesplit(args):
+    """configs[4]: ONE 1-hour 44.1 kHz clip, Griffin-Lim 32 it, frames split by time across the
+    ranks, two 2816-float partials exchanged per boundary per iteration over NCCL (side measurement,
+    printed as its own JSON line with "workload": "timesplit")."""
+    rank, local_rank, world = dist_env()
+    use_dist = world > 1
+    if use_dist:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gomel_b200 import _lib, timesplit
+    from util import synth_clip
+    ctx = _lib.Context(local_rank)
+    cfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
+    ctx.set_mel_tables(cfg, 0.0, 16000.0)
+    n_total = int(round(args.seconds * SR))
+    _, frames_total, ola = _lib.frames(cfg, n_total)
+    # spectrogram: a 60 s synthetic clip's mel (GPU ToMel) repeated along time
+    base_n = 60 * SR
+    wav = synth_clip(9000, 60.0).astype(np.float32)[None, :]
+    _, base_frames, _ = _lib.frames(cfg, base_n)
+    base_mel = np.empty((1, base_frames * N_MELS * 2), np.float32)
+    ctx.check(ctx.lib.gomel_to_mel_batch_host(ctx.h, C.byref(cfg), wav.ctypes.data_as(C.c_void_p), 1, base_n,
+                                              base_mel.ctypes.data_as(C.c_void_p), 1))
+    base_mel = base_mel.reshape(base_frames, N_MELS * 2)
+    s = timesplit.Session(ctx, cfg, frames_total, rank, world, args.ts_tile)
+    idx = (np.arange(s.frame_begin, s.frame_begin + s.n_frames) % base_frames)
+    s.load(base_mel[idx].reshape(-1, 2), None, seed=9001)
+    exchange = timesplit.NcclExchange(s) if use_dist else (lambda it: None)
+
+    def barrier():
+        s.sync()
+        if use_dist:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    it = 0
+    for _ in range(args.warmup):
+        for _ in range(GL_ITERS):
+            if args.ts_overlap:
+                s.iterate(it, 1); exchange(it); s.iterate(it, 2)
+            else:
+                s.iterate(it, 0); exchange(it)
+            it += 1
+    barrier()
+    launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(GL_ITERS):
+            if args.ts_overlap:
+                s.iterate(it, 1); exchange(it); s.iterate(it, 2)
+            else:
+                s.iterate(it, 0); exchange(it)
+            it += 1
+    s.sync()
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    launches = ctx.launch_count() - launches0
+    if use_dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    s.close()
+    if rank == 0:
+        audio_s = frames_total * HOP / SR
+        peak, peak_src = peaks()
+        fi = frames_total * GL_ITERS * args.steps / (ms / 1e3)
+        print(json.dumps({
+            "workload": "timesplit", "metric": METRIC, "value": audio_s * args.steps / (ms / 1e3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "ms_per_iteration": ms / args.steps / GL_ITERS, "higher_is_better": True, "scaling": "strong",
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[4]: one {args.seconds:.0f} s 44.1 kHz clip ({frames_total} frames), Griffin-Lim "
+                                   f"{GL_ITERS} it, frames split by time over {world} GPU(s), NCCL exchange of two 2816-float "
+                                   f"partials per boundary per iteration, tile {args.ts_tile} frames, overlap={bool(args.ts_overlap)}",
+                       "timing": "host wall clock around stream-synchronised region, max over ranks"},
+            "frame_iterations_per_s": fi, "hbm_frac_whole_job": fi * BYTES_PER_FRAME_ITER / 1e9 / (peak * world),
+            "gpu_launches": int(launches)}))
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def bench_to_mel(ctx, cfg, _lib, args):
     """configs[1]: batched ToMel on 256 synthetic 10 s clips (STFT + mel projection only)."""
     from util import synth_clip
@@ -360,11 +447,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stft", dest="stft", action="store_false", help="skip the ToMel side measurement")
     ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")
+    ap.add_argument("--workload", default="clips", choices=["clips", "timesplit"])
+    ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
+    ap.add_argument("--ts-tile", type=int, default=16, help="timesplit: frames per tile")
+    ap.add_argument("--no-ts-overlap", dest="ts_overlap", action="store_false")
     args = ap.parse_args()
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "timesplit":
+        return run_timesplit(args)
     return run_product(args)
 
 

@@ -1081,6 +1081,17 @@ int gomel_ts_finish(gomel_ts* ts, int iters, float* d_out_local)
     return 0;
 }
 
+int gomel_ts_sync(gomel_ts* ts)
+{
+    if (!ts) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    CU(cudaStreamSynchronize(ts->st_edge));
+    CU(cudaStreamSynchronize(ts->st_comm));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
 int gomel_copy_d2d(gomel_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream)
 {
     if (!ctx) return GOMEL_E_ARG;

@@ -83,6 +83,9 @@ class Session:
     def comm_end(self, it):
         self.ctx.check(self.ctx.lib.gomel_ts_comm_end(self.h, it))
 
+    def sync(self):
+        self.ctx.check(self.ctx.lib.gomel_ts_sync(self.h))
+
     def finish(self, iters):
         """-> this rank's local signal (n_samples float32); samples [0, n_frames*Window) are owned by
         this rank (the last rank also owns the final 2816)."""

@@ -171,6 +171,7 @@ int  gomel_ts_comm_begin(gomel_ts *ts, int iter);          /* comm stream waits 
 int  gomel_ts_comm_end(gomel_ts *ts, int iter);            /* marks the exchange of iteration iter done */
 /* folds the last partials in and copies the local signal (n_samples_local floats) to d_out_local */
 int  gomel_ts_finish(gomel_ts *ts, int iters, float *d_out_local);
+int  gomel_ts_sync(gomel_ts *ts);                          /* host waits for all three streams of the session */
 int  gomel_copy_d2d(gomel_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream /* NULL = ctx stream */);
 
 /* ---- pipelined host batch (end-to-end: pinned host float32 in, float32 out, H2D/compute/D2H

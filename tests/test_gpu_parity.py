@@ -325,3 +325,18 @@ def test_timesplit_emulated_ranks_match_single_gpu(mctx, lib, oracle, world, ove
     assert np.array_equal(split.astype(np.float64), whole)
     ref = oracle.from_mel(oracle.config(gl_iters=iters), mel, init.astype(np.float32).astype(np.float64))
     assert rel_l2(split, ref) < TOL_GL
+
+
+def test_timesplit_real_nccl_when_two_gpus():
+    """the NCCL halo exchange itself needs >= 2 GPUs (gpurun --gpus 2); on one GPU the multi-rank
+    path is covered by test_timesplit_emulated_ranks_match_single_gpu"""
+    import subprocess
+    import sys
+    n = int(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU "))
+    if n < 2:
+        pytest.skip("one GPU visible")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(os.path.dirname(__file__), "run_timesplit_nccl.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "TIMESPLIT_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
