@@ -81,6 +81,19 @@ out["f16_in"] = vals
 out["f16_bytes"] = np.frombuffer(b"".join(RP.pack_float16_to_bytes(v) for v in vals), np.uint8)
 out["f16_back"] = np.array([RP.unpack_bytes_to_float64(bytes(out["f16_bytes"][2 * i:2 * i + 2])) for i in range(len(vals))])
 
+# --- save_image / load_image, 8-bit, with and without asinh passes (phase.py:643-852)
+import tempfile  # noqa: E402
+from PIL import Image as _PILImage  # noqa: E402
+for tag, ihs in (("img0", 0), ("img2", 2)):
+    spec = out["c48k_short_spec"]
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "x.png")
+        RP.save_image(f, spec.copy(), 768, 1289.4, 48000, True, False, ihs)
+        out[f"{tag}_pixels"] = np.array(_PILImage.open(f).convert("RGB"), np.uint8)
+        buf, samples, sr, nf = RP.load_image(f, True, False, ihs)
+        out[f"{tag}_loaded"] = buf
+        out[f"{tag}_meta"] = np.array([samples, sr, nf], np.float64)
+
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "phase_ref.npz")
 np.savez_compressed(dst, **out)
 print("wrote", dst, os.path.getsize(dst), "bytes;", len(out), "arrays")

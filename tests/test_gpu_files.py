@@ -1,0 +1,140 @@
+"""GPU tests of the file-level API: WAV -> PNG -> WAV through the drop-in
+classes, PNG pixel bytes against the oracle and against pixels written by the reference's own
+phase.py (tests/golden), float16 metadata, trimming rules."""
+import os
+
+import numpy as np
+import pytest
+
+from util import rel_l2, synth_clip
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "phase_ref.npz")
+
+
+def _mel():
+    from gomel_b200 import NewMel
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut, m.YReverse = 192, 0, 16000, 1280, 4096, True
+    m.GriffinLimIterations, m.VolumeBoost = 2, 0.0
+    return m
+
+
+def test_tomelwav_png_pixels_match_oracle(tmp_path, oracle, ctx):
+    """cmd/tomel configuration: ToMelWav writes the PNG the reference would (<= 1 LSB on boundary pixels)."""
+    from gomel_b200 import codec
+    wav = synth_clip(70, 2.0)
+    wf, pf = str(tmp_path / "a.wav"), str(tmp_path / "a.png")
+    codec.save_wav(wf, wav, 44100)
+    buf, sr = codec.load_wav(wf)
+    m = _mel()
+    m.ToMelWav(wf, pf)
+    px = codec.read_png(pf)
+    ref_mel = oracle.to_mel(oracle.config(), buf)
+    frames = len(ref_mel) // 192
+    assert px.shape == (192, frames, 3)
+    ref_px = oracle.mel_quantise(ref_mel, 192, True, float(len(buf) * 192) / float(len(ref_mel)), float(sr))
+    d = np.abs(px[:, :, :2].astype(int) - ref_px[:, :, :2].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3              # fp32 mel vs float64 mel: boundary pixels only
+    assert np.array_equal(px[:, 1:, 2], ref_px[:, 1:, 2])       # blue: zero except metadata column
+    meta_ours, meta_ref = px[:8, 0, 2], ref_px[:8, 0, 2]        # y-reversed: metadata at the top-left
+    assert np.array_equal(meta_ours[4:], meta_ref[4:])          # samples_in_mel, sample rate bytes
+    assert np.abs(meta_ours[:4].astype(int) - meta_ref[:4].astype(int)).max() <= 1   # max/min float16 of fp32-vs-f64
+
+
+def test_towavpng_matches_oracle_pipeline(tmp_path, oracle, ctx):
+    from gomel_b200 import codec
+    wav = synth_clip(71, 1.5)
+    wf, pf, of = str(tmp_path / "b.wav"), str(tmp_path / "b.png"), str(tmp_path / "b_out.wav")
+    codec.save_wav(wf, wav, 44100)
+    m = _mel()
+    m.ToMelWav(wf, pf)
+    # decode parity: device de-quantisation == oracle loadpng arithmetic on the same pixels, bit for bit
+    px = codec.read_png(pf)
+    rgba = np.concatenate([px, np.full(px.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    obuf, osamples, osr = oracle.mel_dequantise(rgba, True)
+    buf, samples, sr = codec.mel_load_png(pf, True)
+    assert np.array_equal(buf, obuf) and samples == osamples and sr == osr == 44096.0
+    # full ToWavPng with an injected start signal
+    frames = len(buf) // 192
+    ola = 4096 + (frames - 1) * 1280
+    init = np.random.default_rng(2).random(ola)
+    m.InitSignal = init
+    m.VolumeBoost = 0.25
+    m.SampleRate = 0
+    m.ToWavPng(pf, of)
+    assert m.SampleRate == 44096                                 # embedded float16 rate (mel/mel.go:231-233)
+    got, got_sr = codec.load_wav(of)
+    ref = oracle.from_mel(oracle.config(gl_iters=2), obuf + 0.25, init)
+    if int(osamples) > 0 and oracle.is_padded(int(osamples), len(ref), 1280) and len(ref) > int(osamples):
+        ref = ref[:int(osamples)]
+    assert len(got) == len(ref)
+    ref16 = np.clip(ref, -1, 1)
+    assert np.abs(got * 32767.0 - ref16 * 32767.0).max() <= 1.5  # one 16-bit LSB
+
+
+@pytest.mark.parametrize("ihs", [0, 2])
+def test_phase_py_png_matches_reference_pixels(tmp_path, ihs, ctx):
+    """pixels written by the reference's own save_image / values read by its load_image (golden)"""
+    from gomel_b200 import codec
+    from gomel_b200 import phase as P
+    g = np.load(GOLD)
+    f = str(tmp_path / "p.png")
+    P.save_image(f, g["c48k_short_spec"], 768, 1289.4, 48000, True, False, ihs)
+    px = codec.read_png(f)
+    ref = g[f"img{ihs}_pixels"]
+    assert px.shape == ref.shape
+    d = np.abs(px.astype(int) - ref.astype(int))
+    if ihs == 0:
+        assert d.max() == 0                                      # bit-exact
+    else:
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3            # asinh: libm vs CUDA ulps on boundary pixels
+    buf, samples, sr, nf = P.load_image(f, True, False, ihs)
+    assert (samples, sr, nf) == tuple(g[f"img{ihs}_meta"])
+    if ihs == 0:
+        assert np.array_equal(buf, g["img0_loaded"])
+    else:
+        assert rel_l2(buf, g["img2_loaded"]) < 1e-2              # differs only where a pixel moved by 1 LSB
+
+
+@pytest.mark.parametrize("hdr,ihs", [(False, 0), (True, 0), (False, 2)])
+def test_phase_go_png_matches_oracle(tmp_path, oracle, ctx, hdr, ihs):
+    from gomel_b200 import codec
+    rng = np.random.default_rng(5)
+    spec = rng.standard_normal((768 * 7, 2)) * 20
+    f = str(tmp_path / "g.png")
+    codec.phase_dump_image_go(f, spec, 768, True, 1289.4, 48000.0, ihs, hdr)
+    px = codec.read_png(f)
+    ref = oracle.phase_quantise(spec, 768, True, 1289.4, 48000.0, ihs, hdr)
+    d = np.abs(px.astype(int) - ref[:, :, :3].astype(int))
+    if ihs == 0:
+        assert d.max() == 0 and px.dtype == (np.uint16 if hdr else np.uint8)
+    else:
+        assert d[:, :, :2].max() <= 1
+    pad = np.full(px.shape[:2] + (1,), 65535 if hdr else 255, px.dtype)
+    obuf, osamples, osr = oracle.phase_dequantise(np.concatenate([px, pad], axis=2), True, ihs, hdr)
+    buf, samples, sr = codec.phase_load_png_go(f, True, ihs, hdr)
+    assert samples == osamples and sr == osr
+    assert rel_l2(buf, obuf) < 1e-14
+
+
+def test_phase_file_roundtrip(tmp_path, oracle, ctx):
+    from gomel_b200 import Phase, codec
+    wav = synth_clip(72, 1.2, sr=48000)
+    wf, pf, of = str(tmp_path / "c.wav"), str(tmp_path / "c.png"), str(tmp_path / "c_out.wav")
+    codec.save_wav(wf, wav, 48000)
+    ph = Phase()
+    ph.to_phase_wav(wf, pf)
+    assert ph.num_freqs == 768
+    rate = Phase().to_wav_png(pf, of)
+    assert rate == 48000
+    out, sr = codec.load_wav(of)
+    frames = int((len(wav) + codec.pad_len(len(wav), 1280) - 4096) / 1280) + 1
+    assert sr == 48000 and len(out) == min(4096 + (frames - 1) * 1280, len(wav))   # trimmed only if longer (phase.py:343)
+    # 22.05 kHz input: zero-stuffed to 44.1 kHz, 836 bins
+    wav2 = synth_clip(73, 1.0, sr=22050)
+    codec.save_wav(wf, wav2, 22050)
+    ph2 = Phase()
+    ph2.to_phase_wav(wf, pf)
+    assert ph2.num_freqs == 836
+    assert Phase().to_wav_png(pf, of) == 22050                   # nearest standard rate to the float16 value
