@@ -14,8 +14,8 @@
 //        thread (k0,k1), slot k2  <->  bin k = k0 + 16*k1 + 256*k2.
 //  * the exchange buffer is used IN PLACE: every thread always writes exactly the logical cells
 //    it read last, so one __syncthreads per exchange (RAW only) is enough.  Physical address of
-//    logical cell L is L + (L>>4) (one pad per 16), which makes all three access patterns
-//    bank-conflict free with compile-time slot offsets.
+//    logical cell L is L + 2*(L>>4) (two pads per 16), which makes all three access patterns
+//    bank-conflict free with compile-time slot offsets -- pattern (c) with 128-bit accesses.
 //  * bins k and 4096-k (needed together to split the two real spectra) are mapped to lanes of
 //    the same warp, so that split is done with warp shuffles, not another smem pass.
 #pragma once
@@ -26,13 +26,15 @@ namespace gomel {
 
 constexpr int kN = 4096;          // Resolut
 constexpr int kThreads = 256;     // threads per CTA = points / 16
-constexpr int kXchgCells = 16 * 272;                       // padded float2 cells
-constexpr int kXchgBytes = kXchgCells * 8;                 // 34,816 B
-constexpr int kT1Cells = 15 * 256;                         // W4096^(t*k0), k0 = 1..15
-constexpr int kT2Cells = 16 * 16;                          // W256^(n0*k1)
+constexpr int kRow = 18;                                   // float2 cells per 16-cell row (2 pad)
+constexpr int kPlane = 16 * kRow;                          // cells per k0 plane (288)
+constexpr int kXchgCells = 16 * kPlane;                    // padded float2 cells
+constexpr int kXchgBytes = kXchgCells * 8;                 // 36,864 B
+constexpr int kT1Cells = 16 * 256;                         // W4096^(t*k0), k0 = 0..15, as [k0/2][t][k0&1]
+constexpr int kT2Cells = 16 * 16;                          // W256^(n0*k1), as [k1/2][n0][k1&1]
 constexpr int kWinCells = 4096;                            // window, [m][t]
 constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 49,152 B
-constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 83,968 B
+constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 86,016 B
 
 struct Smem {
     float2* T1;     // [15][256]
@@ -62,9 +64,9 @@ __device__ __forceinline__ void load_tables(const Smem& s, const float4* __restr
 // per-thread indices for the three exchange patterns and the spectrum layout
 struct Lanes {
     int t;         // thread id; pattern (a): cell k0*272 + base_a
-    int base_a;    // t + (t>>4)
-    int base_b;    // pattern (b): thread (k0=t>>4, n0=t&15), slot r: base_b + r*17
-    int base_c;    // pattern (c): thread (k0c,k1c), slot n0: base_c + n0
+    int base_a;    // t + 2*(t>>4); slot k0: + k0*kPlane
+    int base_b;    // pattern (b): thread (k0=t>>4, n0=t&15), slot r: base_b + r*kRow
+    int base_c;    // pattern (c): thread (k0c,k1c), slot n0: base_c + n0   (even -> 16-byte aligned)
     int k0c, k1c;  // spectrum digits owned after the forward transform
     int klow;      // k0c + 16*k1c : bins k = klow + 256*k2
     int src;       // lane holding bins 4096-k (partner)
@@ -76,11 +78,11 @@ __device__ __forceinline__ Lanes make_lanes()
     Lanes L;
     const int t = threadIdx.x, w = t >> 5, l = t & 31;
     L.t = t;
-    L.base_a = t + (t >> 4);
-    L.base_b = (t >> 4) * 272 + (t & 15);
+    L.base_a = t + 2 * (t >> 4);
+    L.base_b = (t >> 4) * kPlane + (t & 15);
     if (l < 16) { L.k0c = w; L.k1c = l; }
     else        { L.k0c = (w == 0) ? 8 : 16 - w; L.k1c = 31 - l; }
-    L.base_c = L.k0c * 272 + L.k1c * 17;
+    L.base_c = L.k0c * kPlane + L.k1c * kRow;
     L.klow = L.k0c + 16 * L.k1c;
     if (w == 0) L.src = (l < 16) ? ((16 - l) & 15) : (47 - l);
     else        L.src = l ^ 16;
@@ -127,27 +129,99 @@ __device__ __forceinline__ float2 mul_w16(float2 a)
     /* E == 9 */ return INV ? cmul(a, -c1, -s1) : cmul(a, -c1, s1);
 }
 
+// 4-point DFT whose inputs b1 = h*u1 and b3 = h*u3 carry a pending factor h = sqrt(1/2)
+template <bool INV>
+__device__ __forceinline__ void radix4_h13(float2& a0, float2& u1, float2& a2, float2& u3)
+{
+    constexpr float h = 0.70710678118654752f;
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), s2 = cadd(u1, u3), s3 = csub(u1, u3);
+    a0 = make_float2(fmaf(h, s2.x, t0.x), fmaf(h, s2.y, t0.y));
+    a2 = make_float2(fmaf(-h, s2.x, t0.x), fmaf(-h, s2.y, t0.y));
+    if (!INV) { u1 = make_float2(fmaf(h, s3.y, t1.x), fmaf(-h, s3.x, t1.y)); u3 = make_float2(fmaf(-h, s3.y, t1.x), fmaf(h, s3.x, t1.y)); }
+    else      { u1 = make_float2(fmaf(-h, s3.y, t1.x), fmaf(h, s3.x, t1.y)); u3 = make_float2(fmaf(h, s3.y, t1.x), fmaf(-h, s3.x, t1.y)); }
+}
+// 4-point DFT whose input b2 = h*u2 carries a pending factor h
+template <bool INV>
+__device__ __forceinline__ void radix4_h2(float2& a0, float2& a1, float2& u2, float2& a3)
+{
+    constexpr float h = 0.70710678118654752f;
+    const float2 t0 = make_float2(fmaf(h, u2.x, a0.x), fmaf(h, u2.y, a0.y));
+    const float2 t1 = make_float2(fmaf(-h, u2.x, a0.x), fmaf(-h, u2.y, a0.y));
+    const float2 t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    a0 = cadd(t0, t2);
+    u2 = csub(t0, t2);
+    if (!INV) { a1 = make_float2(t1.x + t3.y, t1.y - t3.x); a3 = make_float2(t1.x - t3.y, t1.y + t3.x); }
+    else      { a1 = make_float2(t1.x - t3.y, t1.y + t3.x); a3 = make_float2(t1.x + t3.y, t1.y - t3.x); }
+}
+
 // 16-point DFT in registers, natural order in and out:  v[k] <- sum_m v[m] W16^{mk}
 template <bool INV>
 __device__ __forceinline__ void radix16(float2 (&v)[16])
 {
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
     // step 1: over m1 for each m0 (elements m0, m0+4, m0+8, m0+12) -> B[m0][ka] at v[m0+4ka]
 #pragma unroll
     for (int m0 = 0; m0 < 4; m0++) radix4<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]);
-    // step 2: inner twiddles W16^{m0*ka}
-    v[5]  = mul_w16<INV, 1>(v[5]);   v[9]  = mul_w16<INV, 2>(v[9]);   v[13] = mul_w16<INV, 3>(v[13]);
-    v[6]  = mul_w16<INV, 2>(v[6]);   v[10] = mul_w16<INV, 4>(v[10]);  v[14] = mul_w16<INV, 6>(v[14]);
-    v[7]  = mul_w16<INV, 3>(v[7]);   v[11] = mul_w16<INV, 6>(v[11]);  v[15] = mul_w16<INV, 9>(v[15]);
+    // step 2: inner twiddles W16^{m0*ka}; the four multiples of W16^2 keep their factor sqrt(1/2) pending:
+    //   W16^2 = h(1 -+ i), W16^6 = h(-1 -+ i)   (upper sign forward)
+    v[5]  = mul_w16<INV, 1>(v[5]);   v[13] = mul_w16<INV, 3>(v[13]);
+    v[7]  = mul_w16<INV, 3>(v[7]);   v[15] = mul_w16<INV, 9>(v[15]);
+    v[10] = mul_w16<INV, 4>(v[10]);
+    (void)c1; (void)s1;
+    auto w2 = [](float2 a) { return INV ? make_float2(a.x - a.y, a.x + a.y) : make_float2(a.x + a.y, a.y - a.x); };
+    auto w6 = [](float2 a) { return INV ? make_float2(-(a.x + a.y), a.x - a.y) : make_float2(a.y - a.x, -(a.x + a.y)); };
+    v[6] = w2(v[6]); v[9] = w2(v[9]); v[11] = w6(v[11]); v[14] = w6(v[14]);      // h still pending
     // step 3: over m0 for each ka (elements 4ka .. 4ka+3) -> X[ka + 4kb]
     float2 o[16];
-#pragma unroll
-    for (int ka = 0; ka < 4; ka++) {
-        float2 b0 = v[4 * ka], b1 = v[4 * ka + 1], b2 = v[4 * ka + 2], b3 = v[4 * ka + 3];
+    {
+        float2 b0 = v[0], b1 = v[1], b2 = v[2], b3 = v[3];
         radix4<INV>(b0, b1, b2, b3);
-        o[ka] = b0; o[ka + 4] = b1; o[ka + 8] = b2; o[ka + 12] = b3;
+        o[0] = b0; o[4] = b1; o[8] = b2; o[12] = b3;
+    }
+    {
+        float2 b0 = v[4], b1 = v[5], b2 = v[6], b3 = v[7];
+        radix4_h2<INV>(b0, b1, b2, b3);
+        o[1] = b0; o[5] = b1; o[9] = b2; o[13] = b3;
+    }
+    {
+        float2 b0 = v[8], b1 = v[9], b2 = v[10], b3 = v[11];
+        radix4_h13<INV>(b0, b1, b2, b3);
+        o[2] = b0; o[6] = b1; o[10] = b2; o[14] = b3;
+    }
+    {
+        float2 b0 = v[12], b1 = v[13], b2 = v[14], b3 = v[15];
+        radix4_h2<INV>(b0, b1, b2, b3);
+        o[3] = b0; o[7] = b1; o[11] = b2; o[15] = b3;
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = o[i];
+}
+
+// external twiddles: T[(k>>1)][lane][k&1] read as float4 = two twiddles per shared-memory load
+template <bool INV>
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* T, int rowlen, int lane)
+{
+    const float4* T4 = reinterpret_cast<const float4*>(T);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 w = T4[q * rowlen + lane];
+        if (q > 0) v[2 * q] = cmul_tw<INV>(v[2 * q], make_float2(w.x, w.y));
+        v[2 * q + 1] = cmul_tw<INV>(v[2 * q + 1], make_float2(w.z, w.w));
+    }
+}
+
+// pattern (c): 16 consecutive cells per thread, 16-byte aligned -> 128-bit accesses
+__device__ __forceinline__ void load_c(float2 (&v)[16], const float2* xb, int base_c)
+{
+    const float4* p = reinterpret_cast<const float4*>(xb + base_c);
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const float4 w = p[q]; v[2 * q] = make_float2(w.x, w.y); v[2 * q + 1] = make_float2(w.z, w.w); }
+}
+__device__ __forceinline__ void store_c(const float2 (&v)[16], float2* xb, int base_c)
+{
+    float4* p = reinterpret_cast<float4*>(xb + base_c);
+#pragma unroll
+    for (int q = 0; q < 8; q++) p[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
 }
 
 // ---------------------------------------------------------------- forward transform (DIF)
@@ -156,21 +230,18 @@ __device__ __forceinline__ void radix16(float2 (&v)[16])
 __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<false>(v);                                               // n2 -> k0
+    apply_twiddles<false>(v, s.T1, 256, L.t);                        // W4096^(t*k0)
 #pragma unroll
-    for (int k0 = 1; k0 < 16; k0++) v[k0] = cmul_tw<false>(v[k0], s.T1[(k0 - 1) * 256 + L.t]);
-#pragma unroll
-    for (int k0 = 0; k0 < 16; k0++) s.xb[k0 * 272 + L.base_a] = v[k0];      // pattern (a)
+    for (int k0 = 0; k0 < 16; k0++) s.xb[k0 * kPlane + L.base_a] = v[k0];    // pattern (a)
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * 17];             // pattern (b)
+    for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];           // pattern (b)
     radix16<false>(v);                                               // n1 -> k1
+    apply_twiddles<false>(v, s.T2, 16, L.t & 15);                    // W256^(n0*k1)
 #pragma unroll
-    for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul_tw<false>(v[k1], s.T2[k1 * 16 + (L.t & 15)]);
-#pragma unroll
-    for (int r = 0; r < 16; r++) s.xb[L.base_b + r * 17] = v[r];             // pattern (b), in place
+    for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];           // pattern (b), in place
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 16; c++) v[c] = s.xb[L.base_c + c];                  // pattern (c)
+    load_c(v, s.xb, L.base_c);                                               // pattern (c)
     radix16<false>(v);                                               // n0 -> k2
 }
 
@@ -180,38 +251,35 @@ __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, cons
 __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<true>(v);                                                // k2 -> n0
-#pragma unroll
-    for (int n0 = 1; n0 < 16; n0++) v[n0] = cmul_tw<true>(v[n0], s.T2[n0 * 16 + L.k1c]);
-#pragma unroll
-    for (int c = 0; c < 16; c++) s.xb[L.base_c + c] = v[c];                  // pattern (c), in place
+    apply_twiddles<true>(v, s.T2, 16, L.k1c);                        // conj W256^(n0*k1), table is symmetric
+    store_c(v, s.xb, L.base_c);                                              // pattern (c), in place
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * 17];             // pattern (b)
+    for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];           // pattern (b)
     radix16<true>(v);                                                // k1 -> n1
 #pragma unroll
-    for (int r = 0; r < 16; r++) s.xb[L.base_b + r * 17] = v[r];             // pattern (b), in place
+    for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];           // pattern (b), in place
     __syncthreads();
 #pragma unroll
-    for (int k0 = 0; k0 < 16; k0++) v[k0] = s.xb[k0 * 272 + L.base_a];       // pattern (a)
-#pragma unroll
-    for (int k0 = 1; k0 < 16; k0++) v[k0] = cmul_tw<true>(v[k0], s.T1[(k0 - 1) * 256 + L.t]);
+    for (int k0 = 0; k0 < 16; k0++) v[k0] = s.xb[k0 * kPlane + L.base_a];    // pattern (a)
+    apply_twiddles<true>(v, s.T1, 256, L.t);                         // conj W4096^(t*k0)
     radix16<true>(v);                                                // k0 -> n2
 }
 
 // ---------------------------------------------------------------- partner fetch
-// P[k2] = Z[4096 - k] for the bins this thread holds (k = klow + 256*k2); processes the two
-// slots j and 15-j together.  Generic lanes: partner lane L.src, partner slot 15-k2.
-// The single special thread (klow == 0) pairs with its own slot (16-k2)&15.
+// P = Z[4096 - k] for the bins this thread holds (k = klow + 256*k2): generic lanes take slot 15-k2 of
+// lane L.src.  The shuffles are unconditional (every lane of every warp executes them); only the single
+// special thread (klow == 0, whose partner is its own slot (16-k2)&15) patches the result afterwards.
+__device__ __forceinline__ float2 shfl2(float2 a, int src)
+{
+    return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
+}
 template <bool WARP0>
 __device__ __forceinline__ void fetch_partner(const float2 (&v)[16], int j, const Lanes& L,
                                               float2& p_lo, float2& p_hi, float2& saved)
 {
     // p_lo = partner of slot j, p_hi = partner of slot 15-j
-    float2 a, b;
-    a.x = __shfl_sync(0xffffffffu, v[15 - j].x, L.src);
-    a.y = __shfl_sync(0xffffffffu, v[15 - j].y, L.src);
-    b.x = __shfl_sync(0xffffffffu, v[j].x, L.src);
-    b.y = __shfl_sync(0xffffffffu, v[j].y, L.src);
+    float2 a = shfl2(v[15 - j], L.src), b = shfl2(v[j], L.src);
     if (WARP0) {
         if (L.special) {
             // slot j pairs with original slot 16-j (updated one step ago -> `saved`), j=0 with itself;

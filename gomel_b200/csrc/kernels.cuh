@@ -402,7 +402,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     for (int j = 0; j < SH; j++) nxt[j] = ld((KEEP + j) * 256);
 
     const int idx_lo = mag_pos(L.klow);
-    const int idx_hi = L.klow ? mag_pos(256 - L.klow) : 256;
     const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
     __syncthreads();                // tables + mbarrier init visible
 
@@ -439,31 +438,44 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         }
 
         // magnitude substitution on both frames at once.  With P = Z[N-k]:
-        //   2*XA[k] = Z + conj P,  2*XB[k] = (Z - conj P)/i ; Y = M * X/|X| ; Z' = YA + i*YB
+        //   2*XA[k] = Z + conj P,  2*XB[k] = (Z - conj P)/i ; Y = M * X/|X| ;
+        //   Z'[k] = YA + i*YB ,  Z'[N-k] = conj(YA) + i*conj(YB)
+        // Each thread does this for its LOWER slots (k < 2048) only and hands Z'[N-k] to the partner lane
+        // that owns bin N-k (its slot 15-j): no bin is substituted twice.
         mbar_wait(bar, (unsigned)(pr & 1));
         {
-            const float* __restrict__ mA = smag;
-            const float* __restrict__ mB = smag + kMagStride;
-            float2 saved = make_float2(0.f, 0.f);
+            const float* __restrict__ mA = smag + idx_lo;
+            const float* __restrict__ mB = smag + kMagStride + idx_lo;
+            const bool w0 = (t >> 5) == 0;
+            float2 zs[16];                       // the special thread's untouched spectrum (warp 0 only)
+            if (w0) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) zs[i] = v[i];
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float mAlo = mA[j * 256 + idx_lo], mAhi = mA[j * 256 + idx_hi];
-                const float mBlo = validB ? mB[j * 256 + idx_lo] : 0.0f;
-                const float mBhi = validB ? mB[j * 256 + idx_hi] : 0.0f;
-                float2 plo, phi;
-                if ((t >> 5) == 0) fetch_partner<true>(v, j, L, plo, phi, saved);
-                else               fetch_partner<false>(v, j, L, plo, phi, saved);
-                {
-                    const float2 z = v[j];
-                    const float2 ya = subst_phase(make_float2(z.x + plo.x, z.y - plo.y), mAlo);
-                    const float2 yb = subst_phase(make_float2(z.y + plo.y, plo.x - z.x), mBlo);
+                const float ma = mA[j * 256];
+                const float mb = validB ? mB[j * 256] : 0.0f;
+                const float2 P = shfl2(v[15 - j], L.src);
+                const float2 z = v[j];
+                const float2 ya = subst_phase(make_float2(z.x + P.x, z.y - P.y), ma);
+                const float2 yb = subst_phase(make_float2(z.y + P.y, P.x - z.x), mb);
+                v[j] = make_float2(ya.x - yb.y, ya.y + yb.x);
+                v[15 - j] = shfl2(make_float2(ya.x + yb.y, yb.x - ya.y), L.src);
+            }
+            if (w0 && L.special) {
+                // klow == 0: bins 256*j pair with 256*(16-j) inside this thread; bins 0 and 2048 are self-conjugate
+#pragma unroll
+                for (int j = 0; j <= 8; j++) {
+                    const int jp = (16 - j) & 15;                      // partner slot
+                    const int mi = (j == 8) ? 2048 : j * 256;          // mag_pos(256*j), idx_lo == 0 here
+                    const float ma = smag[mi];
+                    const float mb = validB ? smag[kMagStride + mi] : 0.0f;
+                    const float2 z = zs[j], P = zs[jp];
+                    const float2 ya = subst_phase(make_float2(z.x + P.x, z.y - P.y), ma);
+                    const float2 yb = subst_phase(make_float2(z.y + P.y, P.x - z.x), mb);
                     v[j] = make_float2(ya.x - yb.y, ya.y + yb.x);
-                }
-                {
-                    const float2 z = v[15 - j];
-                    const float2 ya = subst_phase(make_float2(z.x + phi.x, z.y - phi.y), mAhi);
-                    const float2 yb = subst_phase(make_float2(z.y + phi.y, phi.x - z.x), mBhi);
-                    v[15 - j] = make_float2(ya.x - yb.y, ya.y + yb.x);
+                    if (jp != j) v[jp] = make_float2(ya.x + yb.y, yb.x - ya.y);
                 }
             }
         }

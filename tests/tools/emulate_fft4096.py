@@ -12,7 +12,7 @@ def lanes():
     k0c = np.where(l < 16, w, np.where(w == 0, 8, 16 - w))
     k1c = np.where(l < 16, l, 31 - l)
     src = np.where(w == 0, np.where(l < 16, (16 - l) & 15, 47 - l), l ^ 16)
-    return dict(base_a=T + (T >> 4), base_b=(T >> 4) * 272 + (T & 15), base_c=k0c * 272 + k1c * 17,
+    return dict(base_a=T + 2 * (T >> 4), base_b=(T >> 4) * 288 + (T & 15), base_c=k0c * 288 + k1c * 18,
                 k0c=k0c, k1c=k1c, klow=k0c + 16 * k1c, src=src)
 
 
@@ -30,34 +30,34 @@ def tables():
 
 
 def fwd(v, L, T1, T2):
-    xb = np.zeros(16 * 272, complex)
+    xb = np.zeros(16 * 288, complex)
     v = dft16(v, False)
     for k0 in range(1, 16):
         v[:, k0] *= T1[k0 - 1][T]
     for k0 in range(16):
-        xb[k0 * 272 + L['base_a']] = v[:, k0]
-    v = np.stack([xb[L['base_b'] + r * 17] for r in range(16)], axis=1)
+        xb[k0 * 288 + L['base_a']] = v[:, k0]
+    v = np.stack([xb[L['base_b'] + r * 18] for r in range(16)], axis=1)
     v = dft16(v, False)
     for k1 in range(1, 16):
         v[:, k1] *= T2[k1][T & 15]
     for r in range(16):
-        xb[L['base_b'] + r * 17] = v[:, r]
+        xb[L['base_b'] + r * 18] = v[:, r]
     v = np.stack([xb[L['base_c'] + c] for c in range(16)], axis=1)
     return dft16(v, False)
 
 
 def inv(v, L, T1, T2):
-    xb = np.zeros(16 * 272, complex)
+    xb = np.zeros(16 * 288, complex)
     v = dft16(v, True)
     for n0 in range(1, 16):
         v[:, n0] *= np.conj(T2[n0][L['k1c']])
     for c in range(16):
         xb[L['base_c'] + c] = v[:, c]
-    v = np.stack([xb[L['base_b'] + r * 17] for r in range(16)], axis=1)
+    v = np.stack([xb[L['base_b'] + r * 18] for r in range(16)], axis=1)
     v = dft16(v, True)
     for r in range(16):
-        xb[L['base_b'] + r * 17] = v[:, r]
-    v = np.stack([xb[k0 * 272 + L['base_a']] for k0 in range(16)], axis=1)
+        xb[L['base_b'] + r * 18] = v[:, r]
+    v = np.stack([xb[k0 * 288 + L['base_a']] for k0 in range(16)], axis=1)
     for k0 in range(1, 16):
         v[:, k0] *= np.conj(T1[k0 - 1][T])
     return dft16(v, True)
@@ -147,9 +147,8 @@ def main():
     print("GL pair err", np.abs(out.real - ya[n]).max(), np.abs(out.imag - yb[n]).max())
     assert np.abs(out.real - ya[n]).max() < 1e-9 and np.abs(out.imag - yb[n]).max() < 1e-9
     # bank conflicts: each half-warp of a 64-bit access must hit 16 distinct bank pairs
-    for name, base, offs in (("a", L['base_a'], [k0 * 272 for k0 in range(16)]),
-                             ("b", L['base_b'], [r * 17 for r in range(16)]),
-                             ("c", L['base_c'], list(range(16)))):
+    for name, base, offs in (("a", L['base_a'], [k0 * 288 for k0 in range(16)]),
+                             ("b", L['base_b'], [r * 18 for r in range(16)])):
         worst = 1
         for o in offs:
             addr = base + o
@@ -158,6 +157,16 @@ def main():
                 worst = max(worst, 16 // len(set(banks.tolist())))
         print("pattern", name, "worst conflict degree", worst)
         assert worst == 1
+    # pattern (c) uses 128-bit accesses: a quarter-warp (8 lanes x 16 B) must cover 32 distinct banks
+    worst = 1
+    for q in range(8):
+        addr = (L['base_c'] + 2 * q) * 2                       # first 32-bit word of each lane's float4
+        assert np.all(addr % 4 == 0)                           # 16-byte aligned
+        for g8 in range(32):
+            words = np.concatenate([(addr[g8 * 8:(g8 + 1) * 8] + i) % 32 for i in range(4)])
+            worst = max(worst, 32 // len(set(words.tolist())))
+    print("pattern c (128-bit) worst conflict degree", worst)
+    assert worst == 1
     print("OK")
 
 
