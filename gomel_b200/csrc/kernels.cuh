@@ -140,15 +140,27 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
     const long lim = p.tl.sig_len - (long)f0 * H;
     const int t = L.t;
 
-    float raw[NR];
+    float raw[NR], nxt[SH];
 #pragma unroll
     for (int j = 0; j < KEEP; j++) { const long o = j * 256 + t; raw[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
+#pragma unroll
+    for (int j = 0; j < SH; j++) { const long o = (KEEP + j) * 256 + t; nxt[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
     __syncthreads();
 
     for (int pr = 0; pr < npairs; pr++) {
         const long off0 = (long)pr * 2 * H;
 #pragma unroll
-        for (int j = KEEP; j < NR; j++) { const long o = off0 + j * 256 + t; raw[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
+        for (int j = 0; j < SH; j++) raw[KEEP + j] = nxt[j];
+        if (pr + 1 < npairs) {          // prefetch the next pair's new rows; consumed at the top of the next pass
+            const long r0 = off0 + 2 * H + KEEP * 256;
+            if (r0 + SH * 256 <= lim) {
+#pragma unroll
+                for (int j = 0; j < SH; j++) nxt[j] = __ldg(sig + r0 + j * 256 + t);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SH; j++) { const long o = r0 + j * 256 + t; nxt[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
+            }
+        }
         float2 v[16];
 #pragma unroll
         for (int m = 0; m < 16; m++) { const float w = s.win[m * 256 + t]; v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
@@ -508,12 +520,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 // normalisation is data independent: gain tables (1/ws, 1/thr or 1, times VolumeBoost) are built
 // on the host in float64.  Samples shared by two tiles are left un-normalised (partials in
 // sig_out / hb_out) and finished by k_halo_fix.
-__device__ __forceinline__ float gain_at(const SynParams& p, long s_abs, int hop)
+// mid_idx = s_abs mod hop, supplied by the caller (cheap where hop is a compile-time constant)
+__device__ __forceinline__ float gain_at(const SynParams& p, long s_abs, int mid_idx)
 {
     if (s_abs < p.head_len) return __ldg(p.gain_head + s_abs);
     const long tail0 = p.tl.sig_len - p.tail_len;
     if (s_abs >= tail0) return __ldg(p.gain_tail + (s_abs - tail0));
-    return __ldg(p.gain_mid + (int)(s_abs % hop));
+    return __ldg(p.gain_mid + mid_idx);
 }
 
 template <int HS>
@@ -541,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
         if (o >= lim) return;
         if (has_prev && row < HALO) hout[o] = val;                    // head partial
         else if (has_next && row >= tile_len) sout[o] = val;          // tail partial
-        else sout[o] = val * gain_at(p, sbase + o, H);
+        else sout[o] = val * gain_at(p, sbase + o, o % H);      // sbase is a multiple of H
     };
 
     float acc[NR];
@@ -621,7 +634,7 @@ __global__ void k_halo_fix(float* __restrict__ sig, const float* __restrict__ hb
         if (s_abs >= tl.sig_len) continue;
         float* d = sig + (long)clip * tl.sig_stride + s_abs;
         float x = *d + hb[((long)clip * hb_tiles + tile) * halo + o];
-        if (use_gain) x *= gain_at(gp, s_abs, hop);
+        if (use_gain) x *= gain_at(gp, s_abs, (int)(s_abs % hop));
         *d = x;
     }
 }
