@@ -90,13 +90,20 @@ __device__ __forceinline__ Lanes make_lanes()
     return L;
 }
 
-// ---------------------------------------------------------------- complex helpers
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// ---------------------------------------------------------------- complex helpers, packed FP32
+// A complex value is a float2 in an aligned register pair; sm_100 executes FADD2 / FMUL2 / FFMA2 on
+// such pairs with free operand swizzle (.LO_HI), per-lane sign (.NP/.PN), negation and scalar broadcast,
+// so a complex add, "+- i*b", "a + s*b" and half of a complex multiply are ONE issued instruction each.
+// (Same FP32 pipe throughput as two scalar instructions, half the issue slots -- the kernel is issue bound.)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cadd_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }   // a + i*b
+__device__ __forceinline__ float2 csub_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }   // a - i*b
+__device__ __forceinline__ float2 cfma_s(float2 b, float s, float2 a) { return __ffma2_rn(b, make_float2(s, s), a); }   // a + s*b
 // a * (wr + i*wi)
 __device__ __forceinline__ float2 cmul(float2 a, float wr, float wi)
 {
-    return make_float2(fmaf(-a.y, wi, a.x * wr), fmaf(a.y, wr, a.x * wi));
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-wi, wi), __fmul2_rn(a, make_float2(wr, wr)));
 }
 template <bool INV>
 __device__ __forceinline__ float2 cmul_tw(float2 a, float2 w)   // forward: a*w ; inverse: a*conj(w)
@@ -111,66 +118,65 @@ __device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float
     const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
     a0 = cadd(t0, t2);
     a2 = csub(t0, t2);
-    if (!INV) { a1 = make_float2(t1.x + t3.y, t1.y - t3.x); a3 = make_float2(t1.x - t3.y, t1.y + t3.x); }
-    else      { a1 = make_float2(t1.x - t3.y, t1.y + t3.x); a3 = make_float2(t1.x + t3.y, t1.y - t3.x); }
+    if (!INV) { a1 = csub_i(t1, t3); a3 = cadd_i(t1, t3); }
+    else      { a1 = cadd_i(t1, t3); a3 = csub_i(t1, t3); }
 }
 
-// multiply by W16^e (forward) or its conjugate (INV); e in {1,2,3,4,6,9}
+// multiply by W16^e (forward) or its conjugate (INV); e in {1,3,9}
 template <bool INV, int E>
 __device__ __forceinline__ float2 mul_w16(float2 a)
 {
-    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
-    if (E == 0) return a;
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
     if (E == 1) return INV ? cmul(a, c1, s1) : cmul(a, c1, -s1);
-    if (E == 2) return INV ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
     if (E == 3) return INV ? cmul(a, s1, c1) : cmul(a, s1, -c1);
-    if (E == 4) return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
-    if (E == 6) return INV ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
     /* E == 9 */ return INV ? cmul(a, -c1, -s1) : cmul(a, -c1, s1);
 }
 
-// 4-point DFT whose inputs b1 = h*u1 and b3 = h*u3 carry a pending factor h = sqrt(1/2)
+// 4-point DFT over (b0, h*u1, W16^4*r2, h*u3): u1, u3 carry a pending factor h = sqrt(1/2) and r2 the
+// pending rotation W16^4 = -i (forward) / +i (inverse); both are folded into the packed adds
 template <bool INV>
-__device__ __forceinline__ void radix4_h13(float2& a0, float2& u1, float2& a2, float2& u3)
+__device__ __forceinline__ void radix4_h13(float2& a0, float2& u1, float2& r2, float2& u3)
 {
     constexpr float h = 0.70710678118654752f;
-    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), s2 = cadd(u1, u3), s3 = csub(u1, u3);
-    a0 = make_float2(fmaf(h, s2.x, t0.x), fmaf(h, s2.y, t0.y));
-    a2 = make_float2(fmaf(-h, s2.x, t0.x), fmaf(-h, s2.y, t0.y));
-    if (!INV) { u1 = make_float2(fmaf(h, s3.y, t1.x), fmaf(-h, s3.x, t1.y)); u3 = make_float2(fmaf(-h, s3.y, t1.x), fmaf(h, s3.x, t1.y)); }
-    else      { u1 = make_float2(fmaf(-h, s3.y, t1.x), fmaf(h, s3.x, t1.y)); u3 = make_float2(fmaf(h, s3.y, t1.x), fmaf(-h, s3.x, t1.y)); }
+    const float2 t0 = INV ? cadd_i(a0, r2) : csub_i(a0, r2);
+    const float2 t1 = INV ? csub_i(a0, r2) : cadd_i(a0, r2);
+    const float2 s2 = cadd(u1, u3), s3 = csub(u1, u3);
+    a0 = cfma_s(s2, h, t0);
+    r2 = cfma_s(s2, -h, t0);
+    const float2 s3s = make_float2(s3.y, s3.x);
+    if (!INV) { u1 = __ffma2_rn(s3s, make_float2(h, -h), t1); u3 = __ffma2_rn(s3s, make_float2(-h, h), t1); }   // t1 -+ i*h*s3
+    else      { u1 = __ffma2_rn(s3s, make_float2(-h, h), t1); u3 = __ffma2_rn(s3s, make_float2(h, -h), t1); }
 }
 // 4-point DFT whose input b2 = h*u2 carries a pending factor h
 template <bool INV>
 __device__ __forceinline__ void radix4_h2(float2& a0, float2& a1, float2& u2, float2& a3)
 {
     constexpr float h = 0.70710678118654752f;
-    const float2 t0 = make_float2(fmaf(h, u2.x, a0.x), fmaf(h, u2.y, a0.y));
-    const float2 t1 = make_float2(fmaf(-h, u2.x, a0.x), fmaf(-h, u2.y, a0.y));
+    const float2 t0 = cfma_s(u2, h, a0), t1 = cfma_s(u2, -h, a0);
     const float2 t2 = cadd(a1, a3), t3 = csub(a1, a3);
     a0 = cadd(t0, t2);
     u2 = csub(t0, t2);
-    if (!INV) { a1 = make_float2(t1.x + t3.y, t1.y - t3.x); a3 = make_float2(t1.x - t3.y, t1.y + t3.x); }
-    else      { a1 = make_float2(t1.x - t3.y, t1.y + t3.x); a3 = make_float2(t1.x + t3.y, t1.y - t3.x); }
+    if (!INV) { a1 = csub_i(t1, t3); a3 = cadd_i(t1, t3); }
+    else      { a1 = cadd_i(t1, t3); a3 = csub_i(t1, t3); }
 }
 
 // 16-point DFT in registers, natural order in and out:  v[k] <- sum_m v[m] W16^{mk}
 template <bool INV>
 __device__ __forceinline__ void radix16(float2 (&v)[16])
 {
-    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
     // step 1: over m1 for each m0 (elements m0, m0+4, m0+8, m0+12) -> B[m0][ka] at v[m0+4ka]
 #pragma unroll
     for (int m0 = 0; m0 < 4; m0++) radix4<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]);
-    // step 2: inner twiddles W16^{m0*ka}; the four multiples of W16^2 keep their factor sqrt(1/2) pending:
-    //   W16^2 = h(1 -+ i), W16^6 = h(-1 -+ i)   (upper sign forward)
+    // step 2: inner twiddles W16^{m0*ka}.  W16^2 = h(1 -+ i) and W16^6 = h(-1 -+ i) (upper sign forward)
+    // keep their factor h pending, W16^4 = -+i stays pending entirely (folded into step 3)
     v[5]  = mul_w16<INV, 1>(v[5]);   v[13] = mul_w16<INV, 3>(v[13]);
     v[7]  = mul_w16<INV, 3>(v[7]);   v[15] = mul_w16<INV, 9>(v[15]);
-    v[10] = mul_w16<INV, 4>(v[10]);
-    (void)c1; (void)s1;
-    auto w2 = [](float2 a) { return INV ? make_float2(a.x - a.y, a.x + a.y) : make_float2(a.x + a.y, a.y - a.x); };
-    auto w6 = [](float2 a) { return INV ? make_float2(-(a.x + a.y), a.x - a.y) : make_float2(a.y - a.x, -(a.x + a.y)); };
-    v[6] = w2(v[6]); v[9] = w2(v[9]); v[11] = w6(v[11]); v[14] = w6(v[14]);      // h still pending
+    auto w2 = [](float2 a) { return INV ? cadd_i(a, a) : csub_i(a, a); };                           // a(1 -+ i)
+    auto w6 = [](float2 a) {                                                                        // a(-1 -+ i)
+        return INV ? __fadd2_rn(make_float2(-a.x, -a.y), make_float2(-a.y, a.x))
+                   : __fadd2_rn(make_float2(-a.x, -a.y), make_float2(a.y, -a.x));
+    };
+    v[6] = w2(v[6]); v[9] = w2(v[9]); v[11] = w6(v[11]); v[14] = w6(v[14]);
     // step 3: over m0 for each ka (elements 4ka .. 4ka+3) -> X[ka + 4kb]
     float2 o[16];
     {

@@ -342,8 +342,16 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
     const float n = fmaf(X.x, X.x, X.y * X.y);
     const float r = M * rsqrtf(fmaxf(n, 1e-30f));
     const bool ok = n > 1e-30f;
-    return make_float2(ok ? X.x * r : M, ok ? X.y * r : 0.0f);
+    const float2 y = __fmul2_rn(X, make_float2(r, r));
+    return make_float2(ok ? y.x : M, ok ? y.y : 0.0f);
 }
+// the two real spectra riding one complex transform, up to a common factor 2 (P = Z[N-k]):
+//   2*XA = Z + conj P ,  2*XB = (Z - conj P)/i
+__device__ __forceinline__ float2 split_a(float2 z, float2 P) { return __fadd2_rn(z, make_float2(P.x, -P.y)); }
+__device__ __forceinline__ float2 split_b(float2 z, float2 P) { return __fadd2_rn(make_float2(z.y, -z.x), make_float2(P.y, P.x)); }
+// Z'[k] = YA + i*YB ,  Z'[N-k] = conj(YA) + i*conj(YB)
+__device__ __forceinline__ float2 join_lo(float2 ya, float2 yb) { return __fadd2_rn(ya, make_float2(-yb.y, yb.x)); }
+__device__ __forceinline__ float2 join_hi(float2 ya, float2 yb) { return __fadd2_rn(make_float2(ya.x, -ya.y), make_float2(yb.y, yb.x)); }
 
 // ------------------------------------------------------------------ K5: one Griffin-Lim iteration
 // Replaces one pass of the loop body of mel.ISTFT (mel/mel.go:85-136): frame gather x Hann ->
@@ -470,10 +478,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                 const float mb = validB ? mB[j * 256] : 0.0f;
                 const float2 P = shfl2(v[15 - j], L.src);
                 const float2 z = v[j];
-                const float2 ya = subst_phase(make_float2(z.x + P.x, z.y - P.y), ma);
-                const float2 yb = subst_phase(make_float2(z.y + P.y, P.x - z.x), mb);
-                v[j] = make_float2(ya.x - yb.y, ya.y + yb.x);
-                v[15 - j] = shfl2(make_float2(ya.x + yb.y, yb.x - ya.y), L.src);
+                const float2 ya = subst_phase(split_a(z, P), ma);
+                const float2 yb = subst_phase(split_b(z, P), mb);
+                v[j] = join_lo(ya, yb);
+                v[15 - j] = shfl2(join_hi(ya, yb), L.src);
             }
             if (w0 && L.special) {
                 // klow == 0: bins 256*j pair with 256*(16-j) inside this thread; bins 0 and 2048 are self-conjugate
@@ -484,10 +492,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                     const float ma = smag[mi];
                     const float mb = validB ? smag[kMagStride + mi] : 0.0f;
                     const float2 z = zs[j], P = zs[jp];
-                    const float2 ya = subst_phase(make_float2(z.x + P.x, z.y - P.y), ma);
-                    const float2 yb = subst_phase(make_float2(z.y + P.y, P.x - z.x), mb);
-                    v[j] = make_float2(ya.x - yb.y, ya.y + yb.x);
-                    if (jp != j) v[jp] = make_float2(ya.x + yb.y, yb.x - ya.y);
+                    const float2 ya = subst_phase(split_a(z, P), ma);
+                    const float2 yb = subst_phase(split_b(z, P), mb);
+                    v[j] = join_lo(ya, yb);
+                    if (jp != j) v[jp] = join_hi(ya, yb);
                 }
             }
         }
