@@ -181,6 +181,8 @@ def run_product(args):
     ctx = _lib.Context(local_rank)
     cfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
     ctx.set_mel_tables(cfg, 0.0, 16000.0)
+    if args.tile:
+        ctx.set_tile_frames(args.tile)
     clips = args.clips
     n = int(round(CLIP_SECONDS * SR))
     npad, frames, ola = _lib.frames(cfg, n)
@@ -474,6 +476,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stft", dest="stft", action="store_false", help="skip the ToMel side measurement")
     ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")
+    ap.add_argument("--tile", type=int, default=0, help="frames per tile (0 = library heuristic)")
     ap.add_argument("--workload", default="clips", choices=["clips", "timesplit"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
     ap.add_argument("--ts-tile", type=int, default=16, help="timesplit: frames per tile")

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     };
 
     if (t == 0) mbar_init(bar, 1);
-    float raw[NR], acc[NR], nxt[SH];
+    float raw[NR], acc[NR], nxt[SH], win[16];
 #pragma unroll
     for (int j = 0; j < KEEP; j++) { raw[j] = ld(j * 256); acc[j] = 0.0f; }
 #pragma unroll
@@ -424,6 +424,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     const int idx_lo = mag_pos(L.klow);
     const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
     __syncthreads();                // tables + mbarrier init visible
+#pragma unroll
+    for (int m = 0; m < 16; m++) win[m] = s.win[m * 256 + t];
 
     for (int pr = 0; pr < npairs; pr++) {
         const int off0 = pr * 2 * H;
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         for (int j = 0; j < SH; j++) { raw[KEEP + j] = nxt[j]; acc[KEEP + j] = 0.0f; }
         float2 v[16];
 #pragma unroll
-        for (int m = 0; m < 16; m++) { const float w = s.win[m * 256 + t]; v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
+        for (int m = 0; m < 16; m++) v[m] = make_float2(raw[m] * win[m], raw[m + HS] * win[m]);
 #pragma unroll
         for (int j = 0; j < KEEP; j++) raw[j] = raw[j + SH];
 
@@ -502,11 +504,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 
         fft4096_inv(v, s, L);
 
+        // the Hann coefficients are read once per pair: here for the synthesis window, then kept in
+        // registers for the next pair's analysis window (not live across the transforms)
 #pragma unroll
         for (int m = 0; m < 16; m++) {
-            const float w = s.win[m * 256 + t];
-            acc[m] = fmaf(v[m].x, w, acc[m]);
-            acc[m + HS] = fmaf(v[m].y, w, acc[m + HS]);
+            win[m] = s.win[m * 256 + t];
+            acc[m] = fmaf(v[m].x, win[m], acc[m]);
+            acc[m + HS] = fmaf(v[m].y, win[m], acc[m + HS]);
         }
         if (off0 + SH * 256 <= lim && (!has_prev || off0 >= HALO)) {
 #pragma unroll
