@@ -340,3 +340,81 @@ def test_timesplit_real_nccl_when_two_gpus():
                         os.path.join(os.path.dirname(__file__), "run_timesplit_nccl.py")],
                        capture_output=True, text=True, timeout=600)
     assert "TIMESPLIT_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ long iteration counts / adversarial clips
+def _gl_err(mctx, oracle, wav, iters, seed, tile=0):
+    from gomel_b200 import NewMel
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut = 192, 0, 16000, 1280, 4096
+    m.GriffinLimIterations = iters
+    ocfg = oracle.config(gl_iters=iters)
+    mel = oracle.to_mel(ocfg, wav)
+    frames = len(mel) // 192
+    init = np.random.default_rng(seed).random(4096 + (frames - 1) * 1280)
+    m.InitSignal = init
+    mctx.set_tile_frames(tile)
+    got = m.FromMel(mel.copy())
+    mctx.set_tile_frames(0)
+    return rel_l2(got, oracle.from_mel(ocfg, mel, init))
+
+
+def test_from_mel_100_iterations(mctx, oracle):
+    """configs[3] also names 100 iterations: fp32 drift must stay inside 1e-4 (SURVEY hard part 3)"""
+    err = _gl_err(mctx, oracle, synth_clip(14, 0.8), 100, 5003)
+    assert err < TOL_GL, err
+
+
+@pytest.mark.parametrize("kind", ["white_noise", "silence", "impulses"])
+def test_from_mel_adversarial_32_iterations(mctx, oracle, kind):
+    """worst cases for fp32 drift found in the survey: flat / floor-clamped spectra"""
+    rng = np.random.default_rng(8)
+    n = 30000
+    if kind == "white_noise":
+        wav = rng.uniform(-1, 1, n)
+    elif kind == "silence":
+        wav = np.zeros(n)
+    else:
+        wav = np.zeros(n)
+        wav[rng.integers(0, n, 12)] = rng.uniform(-1, 1, 12)
+    err = _gl_err(mctx, oracle, wav, 32, 5004, tile=6)
+    assert err < TOL_GL, (kind, err)
+
+
+def test_full_size_properties(mctx, lib, oracle):
+    """size-independent properties at BASELINE's full clip size (10 s, 342 frames), where the oracle is too
+    slow for a full Griffin-Lim-32 comparison: ToMel against the oracle, tiling invariance of Griffin-Lim
+    (different tile sizes partition the overlap-add differently but must agree to rounding), determinism,
+    linearity of the phase transform and FromPhase(ToPhase(x)) == oracle round trip."""
+    from gomel_b200 import NewMel, Phase
+    wav = synth_clip(0, 10.0)
+    m = NewMel()
+    m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut, m.GriffinLimIterations = 192, 0, 16000, 1280, 4096, 32
+    mel = m.ToMel(wav)
+    assert mel.shape == (342 * 192, 2)
+    assert rel_l2(np.exp(mel), np.exp(oracle.to_mel(oracle.config(), wav))) < TOL_STFT
+    init = np.random.default_rng(5).random(440576)
+    m.InitSignal = init
+    outs = []
+    for tile in (0, 38, 342):
+        mctx.set_tile_frames(tile)
+        outs.append(m.FromMel(mel.copy()))
+    mctx.set_tile_frames(0)
+    assert outs[0].shape == (440576,)
+    # same algorithm, different partial-sum order: Griffin-Lim amplifies 1e-7 perturbations to ~1e-5..1e-4 over
+    # 32 iterations (SURVEY hard part 3), so two valid fp32 runs agree only to the Griffin-Lim tolerance
+    assert rel_l2(outs[1], outs[0]) < TOL_GL and rel_l2(outs[2], outs[0]) < TOL_GL
+    ref = oracle.from_mel(oracle.config(gl_iters=32), oracle.to_mel(oracle.config(), wav) * 0 + mel, init)   # ~20 s of CPU
+    for o in outs:
+        assert rel_l2(o, ref) < TOL_GL, rel_l2(o, ref)
+    mctx.set_tile_frames(38)
+    again = m.FromMel(mel.copy())
+    mctx.set_tile_frames(0)
+    assert np.array_equal(again, outs[1])                                            # deterministic
+    ph = Phase(num_freqs=768)
+    a, b = synth_clip(1, 10.0), synth_clip(2, 10.0)
+    sa, sb, sab = ph.to_phase(a), ph.to_phase(b), ph.to_phase(0.5 * a - 0.25 * b)
+    assert rel_l2(sab, 0.5 * sa - 0.25 * sb) < 1e-5                                   # linearity
+    rt = ph.from_phase(sa)
+    ocfg = oracle.config(num_freqs=768)
+    assert rel_l2(rt, oracle.from_phase(ocfg, oracle.to_phase(ocfg, a))) < TOL_STFT
