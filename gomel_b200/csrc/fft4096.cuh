@@ -30,11 +30,16 @@ constexpr int kRow = 18;                                   // float2 cells per 1
 constexpr int kPlane = 16 * kRow;                          // cells per k0 plane (288)
 constexpr int kXchgCells = 16 * kPlane;                    // padded float2 cells
 constexpr int kXchgBytes = kXchgCells * 8;                 // 36,864 B
-constexpr int kT1Cells = 16 * 256;                         // W4096^(t*k0), k0 = 0..15, as [k0/2][t][k0&1]
-constexpr int kT2Cells = 16 * 16;                          // W256^(n0*k1), as [k1/2][n0][k1&1]
+// External twiddles are powers of one per-thread root: W4096^(t*k0) = (W4096^t)^k0, W256^(n0*k1) = (W256^n0)^k1.
+// kPowTwiddles: tables hold only the powers 1,2,4,8 (float64-accurate); the other eleven are formed by
+// one to three packed complex multiplies.  Trades 3/4 of the twiddle shared-memory traffic (the most loaded
+// resource of the kernel) and 25 KB of shared memory for 22 packed instructions per twiddle stage.
+constexpr bool kPowTwiddles = true;
+constexpr int kT1Cells = (kPowTwiddles ? 4 : 16) * 256;    // [2][t] float4 = (w^1,w^2),(w^4,w^8)  |  [k0/2][t][k0&1]
+constexpr int kT2Cells = (kPowTwiddles ? 4 : 16) * 16;     // same for W256^n0
 constexpr int kWinCells = 4096;                            // window, [m][t]
-constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 49,152 B
-constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 86,016 B
+constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 25,088 B (49,152 B with full tables)
+constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 61,952 B
 
 struct Smem {
     float2* T1;     // [15][256]
@@ -203,16 +208,33 @@ __device__ __forceinline__ void radix16(float2 (&v)[16])
     for (int i = 0; i < 16; i++) v[i] = o[i];
 }
 
-// external twiddles: T[(k>>1)][lane][k&1] read as float4 = two twiddles per shared-memory load
+// external twiddles v[k] *= w^k (forward) or conj(w)^k (inverse), w = this lane's root
 template <bool INV>
 __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* T, int rowlen, int lane)
 {
     const float4* T4 = reinterpret_cast<const float4*>(T);
+    if (kPowTwiddles) {
+        const float4 a = T4[lane], b = T4[rowlen + lane];
+        const float2 w1 = make_float2(a.x, a.y), w2 = make_float2(a.z, a.w), w4 = make_float2(b.x, b.y), w8 = make_float2(b.z, b.w);
+        auto mul = [](float2 x, float2 y) { return cmul(x, y.x, y.y); };
+        v[1] = cmul_tw<INV>(v[1], w1); v[2] = cmul_tw<INV>(v[2], w2); v[4] = cmul_tw<INV>(v[4], w4); v[8] = cmul_tw<INV>(v[8], w8);
+        const float2 w3 = mul(w2, w1);
+        v[3] = cmul_tw<INV>(v[3], w3);
+        { const float2 w5 = mul(w4, w1); v[5] = cmul_tw<INV>(v[5], w5); v[13] = cmul_tw<INV>(v[13], mul(w8, w5)); }
+        { const float2 w6 = mul(w4, w2); v[6] = cmul_tw<INV>(v[6], w6); v[14] = cmul_tw<INV>(v[14], mul(w8, w6)); }
+        { const float2 w7 = mul(w4, w3); v[7] = cmul_tw<INV>(v[7], w7); v[15] = cmul_tw<INV>(v[15], mul(w8, w7)); }
+        v[9] = cmul_tw<INV>(v[9], mul(w8, w1));
+        v[10] = cmul_tw<INV>(v[10], mul(w8, w2));
+        v[11] = cmul_tw<INV>(v[11], mul(w8, w3));
+        v[12] = cmul_tw<INV>(v[12], mul(w8, w4));
+    } else {
+        // T[(k>>1)][lane][k&1]: two twiddles per 128-bit shared-memory load
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const float4 w = T4[q * rowlen + lane];
-        if (q > 0) v[2 * q] = cmul_tw<INV>(v[2 * q], make_float2(w.x, w.y));
-        v[2 * q + 1] = cmul_tw<INV>(v[2 * q + 1], make_float2(w.z, w.w));
+        for (int q = 0; q < 8; q++) {
+            const float4 w = T4[q * rowlen + lane];
+            if (q > 0) v[2 * q] = cmul_tw<INV>(v[2 * q], make_float2(w.x, w.y));
+            v[2 * q + 1] = cmul_tw<INV>(v[2 * q + 1], make_float2(w.z, w.w));
+        }
     }
 }
 
