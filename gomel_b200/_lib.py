@@ -105,9 +105,12 @@ def load():
     return _lib
 
 
+FLAG_F64 = 1          # strict float64 Griffin-Lim (include/gomel_cuda.h GOMEL_FLAG_F64)
+
+
 def make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=2, tune_mul=1.0, tune_add=0.0,
-                volume_boost=0.0):
-    return Config(n_fft, hop, n_mels, n_freqs, gl_iters, tune_mul, tune_add, volume_boost, 0)
+                volume_boost=0.0, flags=0):
+    return Config(n_fft, hop, n_mels, n_freqs, gl_iters, tune_mul, tune_add, volume_boost, flags)
 
 
 def frames(cfg, n_samples):

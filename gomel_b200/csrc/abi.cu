@@ -3,6 +3,7 @@
 // kernels.cuh.  Host code here only sizes, stages and launches.
 #include "../../include/gomel_cuda.h"
 #include "kernels.cuh"
+#include "kernels_f64.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -19,7 +20,7 @@ constexpr int kHS = 5;                       // hop slots: Window / 256 = 1280 /
 constexpr int kHop = 256 * kHS;
 constexpr int kHalo = (16 - kHS) * 256;      // Resolut - Window = 2816 samples shared by adjacent tiles
 
-enum Scratch { S_F64IN = 0, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_F32C, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
+enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_F32C, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
                S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_COUNT };
 
 }  // namespace
@@ -31,6 +32,7 @@ struct gomel_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
     float4* d_tables = nullptr;
+    double* d_tables64 = nullptr;     // strict float64 path (built on first use)
     // mel tables
     int tbl_mels = 0;
     int *d_fwd_lo = nullptr, *d_fwd_hi = nullptr, *d_inv_lo = nullptr, *d_inv_hi = nullptr;
@@ -357,6 +359,71 @@ int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_
     return 0;
 }
 
+// ---- STRICT float64 Griffin-Lim (GOMEL_FLAG_F64): same algorithm, float64 end to end ----------
+int from_mel_f64(gomel_ctx* ctx, const gomel_config* cfg, const double* d_mel, long n_frames, const double* h_init,
+                 unsigned long long seed, double* h_out)
+{
+    using namespace gomel::f64;
+    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
+        return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
+    if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
+    const long ola = kN + (n_frames - 1) * (long)kHop;
+    if (!ctx->d_tables64) {
+        std::vector<double> blob(kTableBytes64 / 8, 0.0);
+        double* T1 = blob.data();
+        double* T2 = T1 + kT1Cells64 * 2;
+        double* win = T2 + kT2Cells64 * 2;
+        const double two_pi = 6.283185307179586476925286766559;
+        const int pw[4] = { 1, 2, 4, 8 };
+        for (int i = 0; i < 4; i++) {
+            for (int t = 0; t < 256; t++) {
+                const double a = two_pi * (double)((t * pw[i]) % 4096) / 4096.0;
+                T1[(i * 256 + t) * 2] = std::cos(a); T1[(i * 256 + t) * 2 + 1] = -std::sin(a);
+            }
+            for (int n0 = 0; n0 < 16; n0++) {
+                const double a = two_pi * (double)((n0 * pw[i]) % 256) / 256.0;
+                T2[(i * 16 + n0) * 2] = std::cos(a); T2[(i * 16 + n0) * 2 + 1] = -std::sin(a);
+            }
+        }
+        for (int n = 0; n < kN; n++) win[n] = 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1)));
+        CU(cudaMalloc(&ctx->d_tables64, kTableBytes64));
+        CU(cudaMemcpy(ctx->d_tables64, blob.data(), kTableBytes64, cudaMemcpyHostToDevice));
+        CU(cudaFuncSetAttribute(k_gl_pair_f64<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes64));
+    }
+    void *sigA, *sigB, *Y, *mags;
+    const long n_pairs = (n_frames + 1) / 2;
+    if (int rc = ensure(ctx, S_SIG64A, (size_t)ola * 8, &sigA)) return rc;
+    if (int rc = ensure(ctx, S_SIG64B, (size_t)ola * 8, &sigB)) return rc;
+    if (int rc = ensure(ctx, S_Y64, (size_t)n_pairs * 2 * kN * 8, &Y)) return rc;
+    if (int rc = ensure(ctx, S_MAGS64, (size_t)n_frames * 2049 * 8, &mags)) return rc;
+    long g = n_frames < 148L * 8 ? n_frames : 148L * 8;
+    k_mags_from_mel_f64<<<(unsigned)g, 256, (size_t)cfg->n_mels * 2 * sizeof(double), ctx->st>>>(
+        d_mel, (double*)mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_frames);
+    ctx->launches++;
+    if (h_init) CU(cudaMemcpyAsync(sigA, h_init, (size_t)ola * 8, cudaMemcpyHostToDevice, ctx->st));
+    else {
+        void* tmp;
+        if (int rc = ensure(ctx, S_F32A, (size_t)ola * 4, &tmp)) return rc;
+        k_fill_uniform<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((float*)tmp, ola, seed);
+        k_f32_to_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const float*)tmp, (double*)sigA, ola, 1.0);
+        ctx->launches += 2;
+    }
+    double *cur = (double*)sigA, *nxt = (double*)sigB;
+    GL64Params p = {};
+    p.tables = ctx->d_tables64; p.mags = (const double*)mags; p.Y = (double*)Y; p.n_frames = (int)n_frames; p.ola = ola;
+    for (int i = 0; i < cfg->gl_iters; i++) {
+        p.sig = cur;
+        k_gl_pair_f64<kHS><<<(unsigned)n_pairs, kThreads, kSmemBytes64, ctx->st>>>(p);
+        k_ola_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const double*)Y, nxt, (int)n_frames, kHop, ola);
+        ctx->launches += 2;
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    CU(cudaMemcpyAsync(h_out, cur, (size_t)ola * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 struct Guard {
     gomel_ctx* c;
     explicit Guard(gomel_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
@@ -414,6 +481,7 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaStreamSynchronize(ctx->st);
     for (int i = 0; i < S_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_tables64);
     cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
     cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
     cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
@@ -542,6 +610,10 @@ int gomel_from_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* mel, l
     if (int rc = ensure(ctx, S_F32B, (size_t)ola * 4, &dout)) return rc;
     if (int rc = ensure(ctx, S_F64OUT, (size_t)ola * 8, &dout64)) return rc;
     CU(cudaMemcpyAsync(dmel, mel, (size_t)n_mel * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (cfg->flags & GOMEL_FLAG_F64) {
+        if (cfg->gl_iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
+        return from_mel_f64(ctx, cfg, (const double*)dmel, n_frames, init_signal, seed, wav_out);
+    }
     if (init_signal) {
         if (int rc = ensure(ctx, S_F64IN2, (size_t)ola * 8, &dinit64)) return rc;
         if (int rc = ensure(ctx, S_F32A, (size_t)ola * 4, &dinit)) return rc;

@@ -43,12 +43,14 @@ class Mel:
         self.Device = 0
         self.InitSignal = None      # ola_len float64 replacing rand.Float64() (mel/mel.go:80-83)
         self.Seed = None
+        self.Strict = False         # True: float64 Griffin-Lim (GOMEL_FLAG_F64) -- the parity instrument
 
     # ---- plumbing
     def _cfg(self):
         return _lib.make_config(n_fft=self.Resolut, hop=self.Window, n_mels=self.NumMels, n_freqs=0,
                                 gl_iters=self.GriffinLimIterations, tune_mul=self.TuneMul,
-                                tune_add=self.TuneAdd, volume_boost=self.VolumeBoost)
+                                tune_add=self.TuneAdd, volume_boost=self.VolumeBoost,
+                                flags=_lib.FLAG_F64 if self.Strict else 0)
 
     def _ctx(self, cfg):
         ctx = _lib.default_context(self.Device)

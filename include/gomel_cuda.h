@@ -46,8 +46,14 @@ typedef struct {
     double tune_mul;     /* TuneMul */
     double tune_add;     /* TuneAdd */
     double volume_boost; /* VolumeBoost (phase: multiplicative, applied iff != 0) */
-    int flags;           /* reserved, 0 */
+    int flags;           /* GOMEL_FLAG_* */
 } gomel_config;
+
+/* STRICT mode for gomel_from_mel: the whole Griffin-Lim loop in float64 (kernels_f64.cuh).  Griffin-Lim is
+ * ill-conditioned: float32 lands 7e-6 .. 3e-4 from the float64 reference after 32 iterations on a 10 s
+ * clip depending on the start signal; this path reproduces the reference to ~1e-12 for any start signal,
+ * at a fraction of the float32 throughput.  Host-buffer API only. */
+#define GOMEL_FLAG_F64 1
 
 /* ---- context ------------------------------------------------------------------------- */
 int  gomel_ctx_create(int device, gomel_ctx **out);
