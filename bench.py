@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gomel_b200", choices=["gomel_b200", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU (default: the named workload)")
-    ap.add_argument("--chunk", type=int, default=128, help="clips per pipeline chunk in the e2e call")
+    ap.add_argument("--chunk", type=int, default=512, help="clips per pipeline chunk in the e2e call")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stft", dest="stft", action="store_false", help="skip the ToMel side measurement")
     ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")

@@ -878,9 +878,25 @@ int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const flo
         CU(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
     }
     int rc = 0;
-    const int n_chunks = (n_clips + cpc - 1) / cpc;
-    for (int c = 0; c < n_chunks && !rc; c++) {
-        const int b = c & 1, c0 = c * cpc, nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+    // chunk schedule: a small first chunk (short pipeline fill), full chunks, then a taper down to 16 clips
+    // (short drain: the last D2H is the only copy that cannot overlap compute)
+    std::vector<int> sizes;
+    {
+        int left = n_clips;
+        const int first = cpc >= 128 ? cpc / 4 : cpc;
+        auto push = [&](int n) { n = n < left ? n : left; if (n > 0) { sizes.push_back(n); left -= n; } };
+        push(first);
+        int taper = 0;
+        for (int t = cpc / 2; t >= 16; t /= 2) taper += t;
+        while (left > taper + cpc) push(cpc);
+        if (left > taper) push(left - taper);
+        for (int t = cpc / 2; t >= 16 && left > 0; t /= 2) push(t);
+        push(left);
+    }
+    const int n_chunks = (int)sizes.size();
+    int c0 = 0;
+    for (int c = 0; c < n_chunks && !rc; c0 += sizes[c], c++) {
+        const int b = c & 1, nc = sizes[c];
         if (c >= 2) cudaStreamWaitEvent(ctx->st_h2d, done[b], 0);        // inputs of chunk c-2 consumed
         cudaMemcpyAsync(dmel[b], mel + (size_t)c0 * mel_per, (size_t)nc * mel_per * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
         if (init) cudaMemcpyAsync(dinit[b], init + (size_t)c0 * ola, (size_t)nc * ola * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
