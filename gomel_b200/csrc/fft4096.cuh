@@ -296,28 +296,10 @@ __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, cons
 
 // ---------------------------------------------------------------- partner fetch
 // P = Z[4096 - k] for the bins this thread holds (k = klow + 256*k2): generic lanes take slot 15-k2 of
-// lane L.src.  The shuffles are unconditional (every lane of every warp executes them); only the single
-// special thread (klow == 0, whose partner is its own slot (16-k2)&15) patches the result afterwards.
+// lane L.src with shfl2().  The shuffles are unconditional (every lane of every warp executes them); only
+// the single special thread (klow == 0, whose partner is its own slot (16-k2)&15) recomputes its bins.
 __device__ __forceinline__ float2 shfl2(float2 a, int src)
 {
     return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
-template <bool WARP0>
-__device__ __forceinline__ void fetch_partner(const float2 (&v)[16], int j, const Lanes& L,
-                                              float2& p_lo, float2& p_hi, float2& saved)
-{
-    // p_lo = partner of slot j, p_hi = partner of slot 15-j
-    float2 a = shfl2(v[15 - j], L.src), b = shfl2(v[j], L.src);
-    if (WARP0) {
-        if (L.special) {
-            // slot j pairs with original slot 16-j (updated one step ago -> `saved`), j=0 with itself;
-            // slot 15-j pairs with slot j+1 (still original)
-            a = (j == 0) ? v[0] : saved;
-            b = v[j + 1 > 15 ? 15 : j + 1];
-        }
-        saved = v[15 - j];      // original value of slot 15-j, needed next step as slot 16-(j+1)
-    }
-    p_lo = a; p_hi = b;
-}
-
 }  // namespace gomel

@@ -103,6 +103,14 @@ struct Tiling {
     long sig_len;        // valid samples per clip (loads beyond read as 0, stores beyond dropped)
 };
 
+// the two real spectra riding one complex transform, up to a common factor 2 (P = Z[N-k]):
+//   2*XA = Z + conj P ,  2*XB = (Z - conj P)/i
+__device__ __forceinline__ float2 split_a(float2 z, float2 P) { return __fadd2_rn(z, make_float2(P.x, -P.y)); }
+__device__ __forceinline__ float2 split_b(float2 z, float2 P) { return __fadd2_rn(make_float2(z.y, -z.x), make_float2(P.y, P.x)); }
+// Z'[k] = YA + i*YB ,  Z'[N-k] = conj(YA) + i*conj(YB)
+__device__ __forceinline__ float2 join_lo(float2 ya, float2 yb) { return __fadd2_rn(ya, make_float2(-yb.y, yb.x)); }
+__device__ __forceinline__ float2 join_hi(float2 ya, float2 yb) { return __fadd2_rn(make_float2(ya.x, -ya.y), make_float2(yb.y, yb.x)); }
+
 // ------------------------------------------------------------------ K1+K2 / K1+K4: STFT forward
 // Replaces gossp STFT.STFT + the magnitude loop + domel + spectral_normalize of mel.ToMel
 // (mel/mel.go:50-70, mel/impl.go:310-345, :410-419)  [MODE_MEL]
@@ -175,19 +183,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
         // split the two real spectra: XA[k] = (Z[k] + conj Z[N-k])/2, XB[k] = (Z[k] - conj Z[N-k])/(2i)
         // only slots k2 < 8 (k < 2048) and the Nyquist bin carry new information
         float2 xa[9], xb[9];
-        {
-            float2 saved = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                float2 plo, phi;
-                if ((t >> 5) == 0) fetch_partner<true>(v, j, L, plo, phi, saved);
-                else               fetch_partner<false>(v, j, L, plo, phi, saved);
-                xa[j] = make_float2(0.5f * (v[j].x + plo.x), 0.5f * (v[j].y - plo.y));
-                xb[j] = make_float2(0.5f * (v[j].y + plo.y), 0.5f * (plo.x - v[j].x));
-                if (j == 7) {   // slot 8: k = klow + 2048, only k = 2048 (special thread) is a new bin
-                    xa[8] = make_float2(0.5f * (v[8].x + phi.x), 0.5f * (v[8].y - phi.y));
-                    xb[8] = make_float2(0.5f * (v[8].y + phi.y), 0.5f * (phi.x - v[8].x));
-                }
+        for (int j = 0; j < 8; j++) {
+            const float2 P = shfl2(v[15 - j], L.src);                     // Z[N-k], unconditional shuffle
+            xa[j] = __fmul2_rn(split_a(v[j], P), make_float2(0.5f, 0.5f));
+            xb[j] = __fmul2_rn(split_b(v[j], P), make_float2(0.5f, 0.5f));
+        }
+        xa[8] = xb[8] = make_float2(0.f, 0.f);
+        if (L.special) {            // klow == 0: bins 256*j pair with 256*(16-j) inside this thread; j = 8 is the Nyquist bin
+#pragma unroll
+            for (int j = 0; j <= 8; j++) {
+                const float2 P = v[(16 - j) & 15];
+                xa[j] = __fmul2_rn(split_a(v[j], P), make_float2(0.5f, 0.5f));
+                xb[j] = __fmul2_rn(split_b(v[j], P), make_float2(0.5f, 0.5f));
             }
         }
 
@@ -206,26 +214,39 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
                 SB[2048 + 128] = sqrtf(xb[8].x * xb[8].x + xb[8].y * xb[8].y);
             }
             __syncthreads();
-            // domel: out[(frame, mel, ch)], ch0 over |X[k]|, ch1 over |X[N-1-k]| = |X[k+1]|
-            const int per_frame = 2 * p.n_mels;
-            float* outp = p.mel_out + ((long)clip * p.tl.n_frames + fA) * per_frame;
-            for (int o = t; o < 2 * per_frame; o += kThreads) {
-                const int fr = o / per_frame, r = o - fr * per_frame, mel = r >> 1, ch = r & 1;
+            // domel (mel/impl.go:310-345): one work item = (frame, mel), both channels in one pass over the band:
+            // ch0 sums |X[k]| for k in [lo,hi), ch1 sums |X[N-1-k]| = |X[k+1]| for the same k.  Items are ordered
+            // widest band first and dealt boustrophedon so every thread gets about the same number of taps.
+            const int n_items = 2 * p.n_mels;
+            float2* outp = reinterpret_cast<float2*>(p.mel_out) + ((long)clip * p.tl.n_frames + fA) * p.n_mels;
+            for (int q = 0; q * kThreads < n_items; q++) {
+                const int i = q * kThreads + ((q & 1) ? kThreads - 1 - t : t);
+                if (i >= n_items) continue;
+                const int fr = i & 1, mel = p.n_mels - 1 - (i >> 1);
                 if (fr == 1 && !validB) continue;
                 const float* S = fr ? SB : SA;
                 const int lo = p.fwd_lo[mel], hi = p.fwd_hi[mel];
-                float total = 0.0f;
+                float t0 = 0.0f, t1 = 0.0f;
                 if (lo + 1 == hi) {
                     const float md = p.fwd_mod[mel];
-                    const int a = lo + ch, b = hi + ch;
-                    total = S[a + (a >> 4)] * (1.0f - md);
-                    total += S[b + (b >> 4)] * md;
-                } else {
-                    for (int k = lo + ch; k < hi + ch; k++) total += S[k + (k >> 4)];
-                    total /= (float)(hi - lo + 1);
+                    const float s0 = S[lo + (lo >> 4)], s1 = S[hi + (hi >> 4)], s2 = S[hi + 1 + ((hi + 1) >> 4)];
+                    t0 = s0 * (1.0f - md); t0 += s1 * md;
+                    t1 = s1 * (1.0f - md); t1 += s2 * md;
+                } else if (hi > lo) {
+                    int idx = lo + (lo >> 4);
+                    float prev = S[idx];
+                    for (int k = lo; k < hi; k++) {          // prev = S[k]; next = S[k+1]
+                        idx += ((k & 15) == 15) ? 2 : 1;
+                        const float nextv = S[idx];
+                        t0 += prev; t1 += nextv;
+                        prev = nextv;
+                    }
+                    const float inv = 1.0f / (float)(hi - lo + 1);
+                    t0 *= inv; t1 *= inv;
                 }
-                total = (total < 1e-5f) ? 1e-5f : total;
-                outp[o] = logf(total);
+                t0 = (t0 < 1e-5f) ? 1e-5f : t0;
+                t1 = (t1 < 1e-5f) ? 1e-5f : t1;
+                outp[(long)fr * p.n_mels + mel] = make_float2(logf(t0), logf(t1));
             }
         } else if (MODE == MODE_PHASE) {
             float2* SA = s.xb;
@@ -345,14 +366,6 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
     const float2 y = __fmul2_rn(X, make_float2(r, r));
     return make_float2(ok ? y.x : M, ok ? y.y : 0.0f);
 }
-// the two real spectra riding one complex transform, up to a common factor 2 (P = Z[N-k]):
-//   2*XA = Z + conj P ,  2*XB = (Z - conj P)/i
-__device__ __forceinline__ float2 split_a(float2 z, float2 P) { return __fadd2_rn(z, make_float2(P.x, -P.y)); }
-__device__ __forceinline__ float2 split_b(float2 z, float2 P) { return __fadd2_rn(make_float2(z.y, -z.x), make_float2(P.y, P.x)); }
-// Z'[k] = YA + i*YB ,  Z'[N-k] = conj(YA) + i*conj(YB)
-__device__ __forceinline__ float2 join_lo(float2 ya, float2 yb) { return __fadd2_rn(ya, make_float2(-yb.y, yb.x)); }
-__device__ __forceinline__ float2 join_hi(float2 ya, float2 yb) { return __fadd2_rn(make_float2(ya.x, -ya.y), make_float2(yb.y, yb.x)); }
-
 // ------------------------------------------------------------------ K5: one Griffin-Lim iteration
 // Replaces one pass of the loop body of mel.ISTFT (mel/mel.go:85-136): frame gather x Hann ->
 // FFTReal -> Rect(|S|, Phase(F)) -> conj symmetry -> IFFT -> x Hann -> overlap-add, NO window-sum
