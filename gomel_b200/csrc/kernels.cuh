@@ -585,6 +585,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     float acc[NR];
 #pragma unroll
     for (int j = 0; j < KEEP; j++) acc[j] = 0.0f;
+    // the first kPre*256 entries of a pair's two spectrogram rows are prefetched into registers one pair ahead
+    constexpr int kPre = 6;                                   // covers NumFreqs <= 768
+    float2 pre[kPre];
+    auto fetch = [&](int pr_) {
+        const int fA_ = f0 + 2 * pr_;
+        const bool vB_ = (fA_ + 1) < p.tl.n_frames;
+        const float2* __restrict__ src_ = p.spec + ((long)clip * p.tl.n_frames + fA_) * nfq;
+#pragma unroll
+        for (int i = 0; i < kPre; i++) {
+            const int o = t + i * kThreads;
+            pre[i] = (o < 2 * nfq && (o < nfq || vB_)) ? __ldg(src_ + o) : make_float2(0.f, 0.f);
+        }
+    };
+    fetch(0);
     __syncthreads();
 
     for (int pr = 0; pr < npairs; pr++) {
@@ -598,11 +612,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
         const float2* __restrict__ src = p.spec + ((long)clip * p.tl.n_frames + fA) * nfq;
         float2* SA = s.xb;
         float2* SB = s.xb + 2176;
-        for (int o = t; o < 2 * nfq; o += kThreads) {
+#pragma unroll
+        for (int i = 0; i < kPre; i++) {
+            const int o = t + i * kThreads;
+            if (o < 2 * nfq) { const int fr = (o >= nfq), e = o - fr * nfq; (fr ? SB : SA)[e + (e >> 4)] = pre[i]; }
+        }
+        for (int o = t + kPre * kThreads; o < 2 * nfq; o += kThreads) {
             const int fr = (o >= nfq), e = o - fr * nfq;
             const float2 x = (fr == 0 || validB) ? __ldg(src + o) : make_float2(0.f, 0.f);
             (fr ? SB : SA)[e + (e >> 4)] = x;
         }
+        if (pr + 1 < npairs) fetch(pr + 1);
         __syncthreads();
         // X[j+1] = complex(realm0, realn1) = (entry.y, entry.x); entries >= n_freqs replicate the last
         // kept one (grow); X[0] = 0; X[2048] keeps only its real part.  Z' = XA + i*XB, scaled by 1/N.
