@@ -105,6 +105,31 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host thread (and therefore its first-touch pinned buffers) to the NUMA node of its GPU,
+    so that the end-to-end H2D/D2H traffic of 8 ranks does not cross the socket interconnect.  Plumbing only."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -178,6 +203,7 @@ def run_product(args):
     from gomel_b200 import _lib
     from util import synth_clip
 
+    numa_node = bind_to_gpu_numa(local_rank) if args.numa else None
     ctx = _lib.Context(local_rank)
     cfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
     ctx.set_mel_tables(cfg, 0.0, 16000.0)
@@ -299,6 +325,7 @@ def run_product(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_mel.nbytes),
                     "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": e2e_ms / args.steps,
                     "api": "gomel_from_mel_batch_host (pinned host float32 in/out, 3-stream pipeline)",
+                    "host_numa_node": numa_node,
                     "checksum": checksum},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stft_frames_per_s": frame_iters * world * args.steps / (dev_ms / 1e3),
@@ -476,6 +503,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stft", dest="stft", action="store_false", help="skip the ToMel side measurement")
     ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")
+    ap.add_argument("--no-numa", dest="numa", action="store_false", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--tile", type=int, default=0, help="frames per tile (0 = library heuristic)")
     ap.add_argument("--workload", default="clips", choices=["clips", "timesplit"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
