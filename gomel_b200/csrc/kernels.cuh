@@ -9,6 +9,7 @@
 // 2*hop/256 finished ones -- exactly the algorithmic bytes of SURVEY.md 8(d).
 #pragma once
 #include "fft4096.cuh"
+#include <type_traits>
 
 namespace gomel {
 
@@ -481,38 +482,41 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         {
             const float* __restrict__ mA = smag + idx_lo;
             const float* __restrict__ mB = smag + kMagStride + idx_lo;
-            const bool w0 = (t >> 5) == 0;
-            float2 zs[16];                       // the special thread's untouched spectrum (warp 0 only)
-            if (w0) {
+            // The one thread with klow == 0 holds bins 256*s, whose Hermitian partners 256*(16-s) sit in ITS OWN
+            // slots (16-s)&15 -- one slot off the generic pattern (15-s).  It rides the generic loop with a one-step
+            // lag: `saved` keeps the original value of the slot the previous step overwrote.  Only warp 0 runs
+            // this variant, so the other warps pay nothing and warp 0 is not late at the next barrier.
+            auto pass = [&](auto warp0_tag) {
+                constexpr bool W0 = decltype(warp0_tag)::value;
+                float2 saved = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 16; i++) zs[i] = v[i];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float ma = mA[j * 256];
-                const float mb = validB ? mB[j * 256] : 0.0f;
-                const float2 P = shfl2(v[15 - j], L.src);
-                const float2 z = v[j];
-                const float2 ya = subst_phase(split_a(z, P), ma);
-                const float2 yb = subst_phase(split_b(z, P), mb);
-                v[j] = join_lo(ya, yb);
-                v[15 - j] = shfl2(join_hi(ya, yb), L.src);
-            }
-            if (w0 && L.special) {
-                // klow == 0: bins 256*j pair with 256*(16-j) inside this thread; bins 0 and 2048 are self-conjugate
-#pragma unroll
-                for (int j = 0; j <= 8; j++) {
-                    const int jp = (16 - j) & 15;                      // partner slot
-                    const int mi = (j == 8) ? 2048 : j * 256;          // mag_pos(256*j), idx_lo == 0 here
-                    const float ma = smag[mi];
-                    const float mb = validB ? smag[kMagStride + mi] : 0.0f;
-                    const float2 z = zs[j], P = zs[jp];
+                for (int j = 0; j < 8; j++) {
+                    const float ma = mA[j * 256];
+                    const float mb = validB ? mB[j * 256] : 0.0f;
+                    float2 P = shfl2(v[15 - j], L.src);
+                    const float2 z = v[j];
+                    if (W0) {
+                        if (L.special) P = (j == 0) ? z : saved;          // original slot 16-j
+                        saved = v[15 - j];                                // original slot 16-(j+1)
+                    }
                     const float2 ya = subst_phase(split_a(z, P), ma);
                     const float2 yb = subst_phase(split_b(z, P), mb);
                     v[j] = join_lo(ya, yb);
-                    if (jp != j) v[jp] = join_hi(ya, yb);
+                    const float2 Wk = join_hi(ya, yb);
+                    v[15 - j] = shfl2(Wk, L.src);
+                    if (W0 && j >= 1) { if (L.special) v[16 - j] = Wk; }
                 }
-            }
+                if (W0) {
+                    if (L.special) {                                      // Nyquist bin 2048: self-conjugate
+                        const float ma = smag[2048];
+                        const float mb = validB ? smag[kMagStride + 2048] : 0.0f;
+                        const float2 ya = subst_phase(split_a(saved, saved), ma);
+                        const float2 yb = subst_phase(split_b(saved, saved), mb);
+                        v[8] = join_lo(ya, yb);
+                    }
+                }
+            };
+            if ((t >> 5) == 0) pass(std::true_type{}); else pass(std::false_type{});
         }
 
         fft4096_inv(v, s, L);
