@@ -360,12 +360,14 @@ struct SynParams {
 
 __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 {
-    // cmplx.Rect(M, cmplx.Phase(X)) = M * X/|X|; Phase(0) = 0 -> (M, 0)   (mel/mel.go:98-102)
-    const float n = fmaf(X.x, X.x, X.y * X.y);
-    const float r = M * rsqrtf(fmaxf(n, 1e-30f));
-    const bool ok = n > 1e-30f;
-    const float2 y = __fmul2_rn(X, make_float2(r, r));
-    return make_float2(ok ? y.x : M, ok ? y.y : 0.0f);
+    // cmplx.Rect(M, cmplx.Phase(X)) = M * X/|X|, and Phase(0) = 0 -> (M, 0)   (mel/mel.go:98-102).
+    // Branch-free: Y = (X + (d,0)) * M / sqrt(|X|^2 + d^2) with d = 1e-18.  For X = 0 this is exactly the
+    // reference's (M, 0); for any X the transforms can produce (|X| >> 1e-10) d is far below one ulp.
+    const float n = fmaf(X.x, X.x, fmaf(X.y, X.y, 1e-36f));
+    const float r = M * rsqrtf(n);
+    float2 y = __fmul2_rn(X, make_float2(r, r));
+    y.x = fmaf(1e-18f, r, y.x);
+    return y;
 }
 // ------------------------------------------------------------------ K5: one Griffin-Lim iteration
 // Replaces one pass of the loop body of mel.ISTFT (mel/mel.go:85-136): frame gather x Hann ->
