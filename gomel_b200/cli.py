@@ -1,0 +1,52 @@
+"""Command-line tools mirroring the reference's cmd/tomel, cmd/towav, cmd/tophase, cmd/fromphase
+(cmd/*/main.go): same positional arguments and the same hard-coded configurations, on the GPU path.
+
+    python -m gomel_b200.cli tomel  file.wav          -> file.wav.png      (cmd/tomel/main.go:21-59)
+    python -m gomel_b200.cli towav  file.png [rate]   -> file.png.wav      (cmd/towav/main.go:27-44)
+    python -m gomel_b200.cli tophase file.wav         -> file.wav.png      (cmd/tophase/main.go:21-55)
+    python -m gomel_b200.cli fromphase file.png       -> file.png.wav      (cmd/fromphase/main.go:20-32)
+"""
+import sys
+
+from .mel import NewMel
+from .phase import Phase
+
+
+def _mel():
+    m = NewMel()                         # cmd/tomel/main.go:24-31, cmd/towav/main.go:30-39
+    m.MelFmin, m.MelFmax, m.YReverse = 0, 16000, True
+    m.Window, m.NumMels, m.Resolut = 1280, 192, 4096
+    m.GriffinLimIterations, m.VolumeBoost = 2, 0.0
+    return m
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) < 2:
+        print(__doc__)
+        return 1
+    tool, name = argv[0], argv[1]
+    try:
+        if tool == "tomel":
+            src = name if name.endswith(".wav") else name + ".wav"
+            _mel().ToMelWav(src, name + ".png" if name.endswith(".wav") else name + ".png")
+        elif tool == "towav":
+            m = _mel()
+            if len(argv) > 2:
+                m.SampleRate = int(argv[2])
+            m.ToWavPng(name, name + ".wav")
+        elif tool == "tophase":
+            Phase().to_phase_wav(name, name + ".png")
+        elif tool == "fromphase":
+            Phase().to_wav_png(name, name + ".wav")
+        else:
+            print(__doc__)
+            return 1
+    except Exception as e:          # the Go mains print the error and exit 1
+        print(f"Error: {e}")
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -129,20 +129,22 @@ void build_fft_tables(std::vector<float>& blob)
     float* win = T2 + kT2Cells * 2;
     const double two_pi = 6.283185307179586476925286766559;
     auto put = [](float* T, int cell, double a) { T[cell * 2 + 0] = (float)std::cos(a); T[cell * 2 + 1] = (float)(-std::sin(a)); };
+    const int pw[4] = { 1, 2, 4, 8 };
+    // power tables: per lane (w^1, w^2) in float4 row 0 and (w^4, w^8) in row 1; full tables: T[(k>>1)][lane][k&1]
     if (kPowTwiddles) {
-        // per lane: (w^1, w^2) in float4 row 0 and (w^4, w^8) in row 1, w = W4096^t resp. W256^n0
-        const int pw[4] = { 1, 2, 4, 8 };
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 4; i++)
             for (int t = 0; t < 256; t++)
                 put(T1, ((i >> 1) * 256 + t) * 2 + (i & 1), two_pi * (double)((t * pw[i]) % 4096) / 4096.0);
-            for (int n0 = 0; n0 < 16; n0++)
-                put(T2, ((i >> 1) * 16 + n0) * 2 + (i & 1), two_pi * (double)((n0 * pw[i]) % 256) / 256.0);
-        }
     } else {
-        // T1[(k0>>1)][t][k0&1] = W4096^(t*k0); T2[(k1>>1)][n0][k1&1] = W256^(n0*k1) (symmetric in n0,k1)
         for (int k0 = 0; k0 < 16; k0++)
             for (int t = 0; t < 256; t++)
                 put(T1, ((k0 >> 1) * 256 + t) * 2 + (k0 & 1), two_pi * (double)((t * k0) % 4096) / 4096.0);
+    }
+    if (kPowT2) {
+        for (int i = 0; i < 4; i++)
+            for (int n0 = 0; n0 < 16; n0++)
+                put(T2, ((i >> 1) * 16 + n0) * 2 + (i & 1), two_pi * (double)((n0 * pw[i]) % 256) / 256.0);
+    } else {
         for (int k1 = 0; k1 < 16; k1++)
             for (int n0 = 0; n0 < 16; n0++)
                 put(T2, ((k1 >> 1) * 16 + n0) * 2 + (k1 & 1), two_pi * (double)((n0 * k1) % 256) / 256.0);

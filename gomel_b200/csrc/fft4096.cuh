@@ -34,9 +34,13 @@ constexpr int kXchgBytes = kXchgCells * 8;                 // 36,864 B
 // kPowTwiddles: tables hold only the powers 1,2,4,8 (float64-accurate); the other eleven are formed by
 // one to three packed complex multiplies.  Trades 3/4 of the twiddle shared-memory traffic (the most loaded
 // resource of the kernel) and 25 KB of shared memory for 22 packed instructions per twiddle stage.
-constexpr bool kPowTwiddles = true;
+constexpr bool kPowTwiddles = true;      // stage-1 twiddles W4096^(t*k0): 32 KB as a full table
+#ifndef GOMEL_POW_T2
+#define GOMEL_POW_T2 1
+#endif
+constexpr bool kPowT2 = GOMEL_POW_T2;     // stage-2 twiddles W256^(n0*k1): 2 KB as a full table
 constexpr int kT1Cells = (kPowTwiddles ? 4 : 16) * 256;    // [2][t] float4 = (w^1,w^2),(w^4,w^8)  |  [k0/2][t][k0&1]
-constexpr int kT2Cells = (kPowTwiddles ? 4 : 16) * 16;     // same for W256^n0
+constexpr int kT2Cells = (kPowT2 ? 4 : 16) * 16;           // same for W256^n0
 constexpr int kWinCells = 4096;                            // window, [m][t]
 constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 25,088 B (49,152 B with full tables)
 constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 61,952 B
@@ -209,11 +213,11 @@ __device__ __forceinline__ void radix16(float2 (&v)[16])
 }
 
 // external twiddles v[k] *= w^k (forward) or conj(w)^k (inverse), w = this lane's root
-template <bool INV>
+template <bool INV, bool POW>
 __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* T, int rowlen, int lane)
 {
     const float4* T4 = reinterpret_cast<const float4*>(T);
-    if (kPowTwiddles) {
+    if (POW) {
         const float4 a = T4[lane], b = T4[rowlen + lane];
         const float2 w1 = make_float2(a.x, a.y), w2 = make_float2(a.z, a.w), w4 = make_float2(b.x, b.y), w8 = make_float2(b.z, b.w);
         auto mul = [](float2 x, float2 y) { return cmul(x, y.x, y.y); };
@@ -258,14 +262,14 @@ __device__ __forceinline__ void store_c(const float2 (&v)[16], float2* xb, int b
 __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<false>(v);                                               // n2 -> k0
-    apply_twiddles<false>(v, s.T1, 256, L.t);                        // W4096^(t*k0)
+    apply_twiddles<false, kPowTwiddles>(v, s.T1, 256, L.t);                        // W4096^(t*k0)
 #pragma unroll
     for (int k0 = 0; k0 < 16; k0++) s.xb[k0 * kPlane + L.base_a] = v[k0];    // pattern (a)
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];           // pattern (b)
     radix16<false>(v);                                               // n1 -> k1
-    apply_twiddles<false>(v, s.T2, 16, L.t & 15);                    // W256^(n0*k1)
+    apply_twiddles<false, kPowT2>(v, s.T2, 16, L.t & 15);                    // W256^(n0*k1)
 #pragma unroll
     for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];           // pattern (b), in place
     __syncthreads();
@@ -279,7 +283,7 @@ __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, cons
 __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<true>(v);                                                // k2 -> n0
-    apply_twiddles<true>(v, s.T2, 16, L.k1c);                        // conj W256^(n0*k1), table is symmetric
+    apply_twiddles<true, kPowT2>(v, s.T2, 16, L.k1c);                        // conj W256^(n0*k1), table is symmetric
     store_c(v, s.xb, L.base_c);                                              // pattern (c), in place
     __syncthreads();
 #pragma unroll
@@ -290,7 +294,7 @@ __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, cons
     __syncthreads();
 #pragma unroll
     for (int k0 = 0; k0 < 16; k0++) v[k0] = s.xb[k0 * kPlane + L.base_a];    // pattern (a)
-    apply_twiddles<true>(v, s.T1, 256, L.t);                         // conj W4096^(t*k0)
+    apply_twiddles<true, kPowTwiddles>(v, s.T1, 256, L.t);                         // conj W4096^(t*k0)
     radix16<true>(v);                                                // k0 -> n2
 }
 
