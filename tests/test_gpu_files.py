@@ -138,3 +138,40 @@ def test_phase_file_roundtrip(tmp_path, oracle, ctx):
     ph2.to_phase_wav(wf, pf)
     assert ph2.num_freqs == 836
     assert Phase().to_wav_png(pf, of) == 22050                   # nearest standard rate to the float16 value
+
+
+def test_config1_old_format_fixture_shape(tmp_path, oracle, ctx):
+    """BASELINE configs[0] names the reference's glados PNG (183 x 80, older 3-channel format, every metadata
+    byte 0x02).  With NumMels = 192 the Go reference panics (14,640 entries are not a multiple of 192,
+    mel/impl.go:366-372): we return an error instead.  With NumMels = 80 the image decodes to the
+    constant 3.06e-5 spectrogram (max == min) and runs the flat-spectrum Griffin-Lim path end to end.
+    The fixture itself is not copied: an image with the same geometry and metadata bytes is synthesised."""
+    from gomel_b200 import NewMel, _lib, codec
+    w, h = 183, 80
+    img = np.zeros((h, w, 3), np.uint8)
+    rng = np.random.default_rng(0)
+    img[:, :, 0] = rng.integers(0, 255, (h, w))
+    img[:, :, 1] = rng.integers(0, 255, (h, w))
+    img[:, :, 2] = 2                                             # every metadata byte 0x02 -> float16 0x0202 = 3.06e-5
+    f = str(tmp_path / "old.png")
+    codec.write_png(f, img)
+    buf, samples, sr = codec.mel_load_png(f, True)
+    assert buf.shape == (w * h, 2) and samples == 0.0 and abs(sr - 3.0637e-5) < 1e-8
+    assert np.all(buf == buf[0, 0]) and abs(buf[0, 0] - 3.0637e-5) < 1e-8     # max == min: constant spectrogram
+    m = NewMel()
+    m.MelFmin, m.MelFmax, m.YReverse, m.Window, m.Resolut, m.GriffinLimIterations = 0, 16000, True, 1280, 4096, 2
+    m.NumMels = 192
+    with pytest.raises(_lib.GomelError):
+        m.ToWavPng(f, str(tmp_path / "x.wav"))                   # the reference panics here
+    m.NumMels = 80
+    init = np.random.default_rng(1).random(4096 + (w - 1) * 1280)
+    m.InitSignal = init
+    got = m.FromMel(buf.copy())
+    assert got.shape == (237056,)                                # SURVEY 8(d): OLA length for 183 frames
+    ocfg = oracle.config(num_mels=80, gl_iters=2)
+    ref = oracle.from_mel(ocfg, buf, init)
+    assert rel_l2(got, ref) < 1e-4
+    m.SampleRate = 44100
+    m.ToWavPng(f, str(tmp_path / "old.wav"))                     # whole file path: PNG -> WAV
+    out, osr = codec.load_wav(str(tmp_path / "old.wav"))
+    assert osr == 44100 and len(out) == 237056
