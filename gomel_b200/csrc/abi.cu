@@ -307,8 +307,9 @@ int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_row
     if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
         return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
     if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
-    long g = n_rows < 148L * 8 ? n_rows : 148L * 8;
-    k_mags_from_mel<T><<<(unsigned)g, 256, (size_t)cfg->n_mels * 2 * sizeof(double), ctx->st>>>(
+    long g = (n_rows + kMagsRowsPerPass - 1) / kMagsRowsPerPass;
+    if (g > 148L * 8) g = 148L * 8;
+    k_mags_from_mel<T><<<(unsigned)g, 256, (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double), ctx->st>>>(
         d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     ctx->launches++;
     CU(cudaGetLastError());

@@ -300,36 +300,44 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
 // :386-408) reduced to the 2049 magnitudes mel.ISTFT actually uses: |X[k]| = ch0[k] for k < 2048
 // and ch1[2047] for k = 2048 (cmplx.Abs at mel/mel.go:99).  Output rows are pre-scaled by 1/N
 // (the IFFT normalisation) and stored in mag_pos() order.  Arithmetic in float64.
+constexpr int kMagsRowsPerPass = 4;       // frames handled together by one CTA pass (amortises the barriers)
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel, float* __restrict__ mags,
                                                        const int* __restrict__ inv_lo, const int* __restrict__ inv_hi,
                                                        const double* __restrict__ inv_mod, int n_mels,
                                                        double tune_add, double tune_mul, long n_rows)
 {
-    extern __shared__ double e[];     // [n_mels][2]
-    for (long row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        const T* m = mel + row * 2 * n_mels;
+    extern __shared__ double e[];     // [kMagsRowsPerPass][n_mels][2]
+    const int per_row = 2 * n_mels;
+    for (long row0 = (long)blockIdx.x * kMagsRowsPerPass; row0 < n_rows; row0 += (long)gridDim.x * kMagsRowsPerPass) {
+        const int nr = (int)((n_rows - row0 < kMagsRowsPerPass) ? n_rows - row0 : kMagsRowsPerPass);
+        const T* m = mel + row0 * per_row;
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * n_mels; i += blockDim.x) e[i] = exp((double)m[i]);
+        for (int i = threadIdx.x; i < nr * per_row; i += blockDim.x) e[i] = exp((double)m[i]);
         __syncthreads();
-        float* out = mags + row * kMagStride;
-        for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes
+        for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes in mag_pos order
             const int i = mag_unpos(pos);
             const int lo = inv_lo[i], hi = inv_hi[i];
-            const int nch = (i == 2047) ? 2 : 1;
-            for (int l = 0; l < nch; l++) {
-                double total = 0.0;
-                if (lo == hi) total = e[2 * lo + l];
-                else if (lo + 1 == hi && hi < n_mels) {
-                    const double md = inv_mod[i];
-                    total = e[2 * lo + l] * (1.0 - md);
-                    total += e[2 * hi + l] * md;
-                } else {
-                    for (int k = lo; k < hi; k++) total += e[2 * k + l];
-                    total /= (double)(hi - lo + 1);
+            const bool copy = lo == hi, lerp = (lo + 1 == hi) && hi < n_mels;
+            const double md = lerp ? inv_mod[i] : 0.0;
+            for (int r = 0; r < nr; r++) {
+                const double* er = e + r * per_row;
+                float* out = mags + (row0 + r) * kMagStride;
+                const int nch = (i == 2047) ? 2 : 1;
+                for (int l = 0; l < nch; l++) {
+                    double total = 0.0;
+                    if (copy) total = er[2 * lo + l];
+                    else if (lerp) {
+                        total = er[2 * lo + l] * (1.0 - md);
+                        total += er[2 * hi + l] * md;
+                    } else {
+                        for (int k = lo; k < hi; k++) total += er[2 * k + l];
+                        total /= (double)(hi - lo + 1);
+                    }
+                    const double v = fabs((total - tune_add) / tune_mul) * (1.0 / 4096.0);
+                    out[l ? 2048 : pos] = (float)v;
                 }
-                const double v = fabs((total - tune_add) / tune_mul) * (1.0 / 4096.0);
-                out[l ? 2048 : pos] = (float)v;
             }
         }
     }
