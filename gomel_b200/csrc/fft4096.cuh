@@ -13,7 +13,9 @@
 //    point-wise stage between them works on the digit-reversed layout
 //        thread (k0,k1), slot k2  <->  bin k = k0 + 16*k1 + 256*k2.
 //  * the exchange buffer is used IN PLACE: every thread always writes exactly the logical cells
-//    it read last, so one __syncthreads per exchange (RAW only) is enough.  Physical address of
+//    it read last, so one barrier per exchange (RAW only) is enough -- and the exchange between
+//    stages 2 and 3 stays inside a half-warp, so it needs only __syncwarp: two CTA barriers per
+//    transform pair instead of four.  Physical address of
 //    logical cell L is L + 2*(L>>4) (two pads per 16), which makes all three access patterns
 //    bank-conflict free with compile-time slot offsets -- pattern (c) with 128-bit accesses.
 //  * bins k and 4096-k (needed together to split the two real spectra) are mapped to lanes of
@@ -74,7 +76,9 @@ __device__ __forceinline__ void load_tables(const Smem& s, const float4* __restr
 struct Lanes {
     int t;         // thread id; pattern (a): cell k0*272 + base_a
     int base_a;    // t + 2*(t>>4); slot k0: + k0*kPlane
-    int base_b;    // pattern (b): thread (k0=t>>4, n0=t&15), slot r: base_b + r*kRow
+    int base_b;    // pattern (b): thread (k0b,n0b), slot r: base_b + r*kRow.  k0b == k0c: the 16 threads that share a
+                   // k0 plane form the same half-warp in stages 2 and 3, so the exchange between those stages is warp-local
+    int n0b;       // n0 digit owned in stage 2 (lane & 15)
     int base_c;    // pattern (c): thread (k0c,k1c), slot n0: base_c + n0   (even -> 16-byte aligned)
     int k0c, k1c;  // spectrum digits owned after the forward transform
     int klow;      // k0c + 16*k1c : bins k = klow + 256*k2
@@ -88,9 +92,10 @@ __device__ __forceinline__ Lanes make_lanes()
     const int t = threadIdx.x, w = t >> 5, l = t & 31;
     L.t = t;
     L.base_a = t + 2 * (t >> 4);
-    L.base_b = (t >> 4) * kPlane + (t & 15);
     if (l < 16) { L.k0c = w; L.k1c = l; }
     else        { L.k0c = (w == 0) ? 8 : 16 - w; L.k1c = 31 - l; }
+    L.n0b = l & 15;
+    L.base_b = L.k0c * kPlane + L.n0b;
     L.base_c = L.k0c * kPlane + L.k1c * kRow;
     L.klow = L.k0c + 16 * L.k1c;
     if (w == 0) L.src = (l < 16) ? ((16 - l) & 15) : (47 - l);
@@ -269,10 +274,10 @@ __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, cons
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];           // pattern (b)
     radix16<false>(v);                                               // n1 -> k1
-    apply_twiddles<false, kPowT2>(v, s.T2, 16, L.t & 15);                    // W256^(n0*k1)
+    apply_twiddles<false, kPowT2>(v, s.T2, 16, L.n0b);                       // W256^(n0*k1)
 #pragma unroll
     for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];           // pattern (b), in place
-    __syncthreads();
+    __syncwarp();                                                    // plane k0 is private to this half-warp
     load_c(v, s.xb, L.base_c);                                               // pattern (c)
     radix16<false>(v);                                               // n0 -> k2
 }
@@ -285,7 +290,7 @@ __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, cons
     radix16<true>(v);                                                // k2 -> n0
     apply_twiddles<true, kPowT2>(v, s.T2, 16, L.k1c);                        // conj W256^(n0*k1), table is symmetric
     store_c(v, s.xb, L.base_c);                                              // pattern (c), in place
-    __syncthreads();
+    __syncwarp();                                                    // plane k0 is private to this half-warp
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];           // pattern (b)
     radix16<true>(v);                                                // k1 -> n1

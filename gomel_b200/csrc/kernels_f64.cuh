@@ -98,7 +98,7 @@ __device__ __forceinline__ void fft_fwd(c64 (&v)[16], const Smem64& s, const Lan
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];
     radix16<false>(v);
-    apply_twiddles<false>(v, s.T2, 16, L.t & 15);
+    apply_twiddles<false>(v, s.T2, 16, L.n0b);
 #pragma unroll
     for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];
     __syncthreads();

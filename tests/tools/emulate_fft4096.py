@@ -12,7 +12,7 @@ def lanes():
     k0c = np.where(l < 16, w, np.where(w == 0, 8, 16 - w))
     k1c = np.where(l < 16, l, 31 - l)
     src = np.where(w == 0, np.where(l < 16, (16 - l) & 15, 47 - l), l ^ 16)
-    return dict(base_a=T + 2 * (T >> 4), base_b=(T >> 4) * 288 + (T & 15), base_c=k0c * 288 + k1c * 18,
+    return dict(base_a=T + 2 * (T >> 4), base_b=k0c * 288 + (l & 15), n0b=l & 15, base_c=k0c * 288 + k1c * 18,
                 k0c=k0c, k1c=k1c, klow=k0c + 16 * k1c, src=src)
 
 
@@ -39,7 +39,7 @@ def fwd(v, L, T1, T2):
     v = np.stack([xb[L['base_b'] + r * 18] for r in range(16)], axis=1)
     v = dft16(v, False)
     for k1 in range(1, 16):
-        v[:, k1] *= T2[k1][T & 15]
+        v[:, k1] *= T2[k1][L['n0b']]
     for r in range(16):
         xb[L['base_b'] + r * 18] = v[:, r]
     v = np.stack([xb[L['base_c'] + c] for c in range(16)], axis=1)
@@ -167,6 +167,15 @@ def main():
             worst = max(worst, 32 // len(set(words.tolist())))
     print("pattern c (128-bit) worst conflict degree", worst)
     assert worst == 1
+    # exchange 2 is warp-local: the cells a thread reads in pattern (c) were written (pattern b) by threads of its own warp
+    owner = {}
+    for t in range(256):
+        for r in range(16):
+            owner[int(L['base_b'][t]) + r * 18] = t >> 5
+    for t in range(256):
+        for c in range(16):
+            assert owner[int(L['base_c'][t]) + c] == t >> 5
+    print("exchange 2 warp-local: OK")
     print("OK")
 
 
