@@ -256,9 +256,12 @@ __device__ __forceinline__ void load_c(float2 (&v)[16], const float2* xb, int ba
 }
 __device__ __forceinline__ void store_c(const float2 (&v)[16], float2* xb, int base_c)
 {
-    float4* p = reinterpret_cast<float4*>(xb + base_c);
+    // 64-bit stores, spelled in PTX so that they are not re-merged: a 128-bit store needs four consecutive
+    // registers and costs four MOVs to assemble them out of two packed-FP32 register pairs
+    const unsigned a = (unsigned)__cvta_generic_to_shared(xb + base_c);
 #pragma unroll
-    for (int q = 0; q < 8; q++) p[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+    for (int c = 0; c < 16; c++)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + 8u * c), "f"(v[c].x), "f"(v[c].y));
 }
 
 // ---------------------------------------------------------------- forward transform (DIF)
