@@ -366,13 +366,19 @@ struct SynParams {
     int ext_prev, ext_next;  // a previous / next rank continues the clip beyond this buffer
 };
 
+__device__ __forceinline__ float rsqrt_fast(float x)       // one MUFU.RSQ; callers guarantee x >= 1e-36 (no denormal path)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 {
     // cmplx.Rect(M, cmplx.Phase(X)) = M * X/|X|, and Phase(0) = 0 -> (M, 0)   (mel/mel.go:98-102).
     // Branch-free: Y = (X + (d,0)) * M / sqrt(|X|^2 + d^2) with d = 1e-18.  For X = 0 this is exactly the
     // reference's (M, 0); for any X the transforms can produce (|X| >> 1e-10) d is far below one ulp.
     const float n = fmaf(X.x, X.x, fmaf(X.y, X.y, 1e-36f));
-    const float r = M * rsqrtf(n);
+    const float r = M * rsqrt_fast(n);
     float2 y = __fmul2_rn(X, make_float2(r, r));
     y.x = fmaf(1e-18f, r, y.x);
     return y;
@@ -386,7 +392,7 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 // sums -- the earlier tile's into sig_out (its tail), the later tile's into hb_out (its head) --
 // and summed on load (a+b is commutative, so both readers see the same value).
 constexpr int kGlMagBytes = 2 * kMagStride * 4;                 // two magnitude rows (frames A and B)
-constexpr int kGlSmemBytes = kSmemBytes + kGlMagBytes + 16;     // + one mbarrier
+constexpr int kGlSmemBytes = kSmemBytes + kGlMagBytes + 16 + 256;   // + one mbarrier + the special coset's scratch
 
 template <int HS>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     const Smem s = carve_smem(smem_raw);
     float* const smag = reinterpret_cast<float*>(smem_raw + kSmemBytes);                 // [2][kMagStride]
     unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + kSmemBytes + kGlMagBytes);
+    float2* const zsc = reinterpret_cast<float2*>(smem_raw + kSmemBytes + kGlMagBytes + 16);   // [2][16]
     const Lanes L = make_lanes();
     load_tables(s, p.tables, L.t);
     constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
@@ -493,40 +500,46 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
             const float* __restrict__ mA = smag + idx_lo;
             const float* __restrict__ mB = smag + kMagStride + idx_lo;
             // The one thread with klow == 0 holds bins 256*s, whose Hermitian partners 256*(16-s) sit in ITS OWN
-            // slots (16-s)&15 -- one slot off the generic pattern (15-s).  It rides the generic loop with a one-step
-            // lag: `saved` keeps the original value of the slot the previous step overwrote.  Only warp 0 runs
-            // this variant, so the other warps pay nothing and warp 0 is not late at the next barrier.
-            auto pass = [&](auto warp0_tag) {
-                constexpr bool W0 = decltype(warp0_tag)::value;
-                float2 saved = make_float2(0.f, 0.f);
+            // slots (16-s)&15 -- off the generic lane pattern.  It parks its 16 values in a 256-byte scratch; lanes
+            // 1..9 of warp 0 each substitute one of the nine special pairs {s, 16-s} after the generic loop and
+            // thread 0 picks the results up again.  Everything stays inside warp 0 (__syncwarp), no code variant.
+            const bool w0 = (t >> 5) == 0;
+            if (w0) {
+                if (L.special) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float ma = mA[j * 256];
-                    const float mb = validB ? mB[j * 256] : 0.0f;
-                    float2 P = shfl2(v[15 - j], L.src);
-                    const float2 z = v[j];
-                    if (W0) {
-                        if (L.special) P = (j == 0) ? z : saved;          // original slot 16-j
-                        saved = v[15 - j];                                // original slot 16-(j+1)
-                    }
+                    for (int i = 0; i < 16; i++) zsc[i] = v[i];
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float ma = mA[j * 256];
+                const float mb = validB ? mB[j * 256] : 0.0f;
+                const float2 P = shfl2(v[15 - j], L.src);
+                const float2 z = v[j];
+                const float2 ya = subst_phase(split_a(z, P), ma);
+                const float2 yb = subst_phase(split_b(z, P), mb);
+                v[j] = join_lo(ya, yb);
+                v[15 - j] = shfl2(join_hi(ya, yb), L.src);
+            }
+            if (w0) {
+                const int j = t - 1;                                   // lanes 1..9 -> special pair j = 0..8
+                if (j >= 0 && j <= 8) {
+                    const int jp = (16 - j) & 15, mi = (j == 8) ? 2048 : j * 256;
+                    const float ma = smag[mi];
+                    const float mb = validB ? smag[kMagStride + mi] : 0.0f;
+                    const float2 z = zsc[j], P = zsc[jp];
                     const float2 ya = subst_phase(split_a(z, P), ma);
                     const float2 yb = subst_phase(split_b(z, P), mb);
-                    v[j] = join_lo(ya, yb);
-                    const float2 Wk = join_hi(ya, yb);
-                    v[15 - j] = shfl2(Wk, L.src);
-                    if (W0 && j >= 1) { if (L.special) v[16 - j] = Wk; }
+                    zsc[16 + j] = join_lo(ya, yb);
+                    if (jp != j) zsc[16 + jp] = join_hi(ya, yb);
                 }
-                if (W0) {
-                    if (L.special) {                                      // Nyquist bin 2048: self-conjugate
-                        const float ma = smag[2048];
-                        const float mb = validB ? smag[kMagStride + 2048] : 0.0f;
-                        const float2 ya = subst_phase(split_a(saved, saved), ma);
-                        const float2 yb = subst_phase(split_b(saved, saved), mb);
-                        v[8] = join_lo(ya, yb);
-                    }
+                __syncwarp();
+                if (L.special) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = zsc[16 + i];
                 }
-            };
-            if ((t >> 5) == 0) pass(std::true_type{}); else pass(std::false_type{});
+            }
         }
 
         fft4096_inv(v, s, L);
