@@ -150,7 +150,7 @@ void build_fft_tables(std::vector<float>& blob)
                 put(T2, ((k1 >> 1) * 16 + n0) * 2 + (k1 & 1), two_pi * (double)((n0 * k1) % 256) / 256.0);
     }
     // symmetric Hann of gossp/go-dsp: 0.5*(1-cos(2 pi n/(N-1)))  (phase.py:122 np.hanning)
-    for (int m = 0; m < 16; m++)
+    for (int m = 0; m < 8; m++)                      // first half only: w[n] = w[4095-n]
         for (int t = 0; t < 256; t++) {
             const int n = t + 256 * m;
             win[m * 256 + t] = (float)(0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1))));

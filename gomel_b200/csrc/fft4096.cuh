@@ -43,7 +43,7 @@ constexpr bool kPowTwiddles = true;      // stage-1 twiddles W4096^(t*k0): 32 KB
 constexpr bool kPowT2 = GOMEL_POW_T2;     // stage-2 twiddles W256^(n0*k1): 2 KB as a full table
 constexpr int kT1Cells = (kPowTwiddles ? 4 : 16) * 256;    // [2][t] float4 = (w^1,w^2),(w^4,w^8)  |  [k0/2][t][k0&1]
 constexpr int kT2Cells = (kPowT2 ? 4 : 16) * 16;           // same for W256^n0
-constexpr int kWinCells = 4096;                            // window, [m][t]
+constexpr int kWinCells = 2048;                            // first half of the symmetric Hann window, [m][t], m < 8
 constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 25,088 B (49,152 B with full tables)
 constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 61,952 B
 
@@ -62,6 +62,13 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base)
     s.win = reinterpret_cast<float*>(s.T2 + kT2Cells);
     s.xb = reinterpret_cast<float2*>(s.win + kWinCells);
     return s;
+}
+
+// Hann coefficient of sample n = t + 256*m.  The window is symmetric (w[n] = w[4095-n]), only its first half is
+// kept in shared memory; both access patterns are unit-stride across a warp.
+__device__ __forceinline__ float win_at(const float* win, int m, int t)
+{
+    return (m < 8) ? win[m * 256 + t] : win[(15 - m) * 256 + (255 - t)];
 }
 
 // global table blob layout == smem table layout (T1 | T2 | win), kTableBytes long

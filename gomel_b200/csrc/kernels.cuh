@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
         }
         float2 v[16];
 #pragma unroll
-        for (int m = 0; m < 16; m++) { const float w = s.win[m * 256 + t]; v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
+        for (int m = 0; m < 16; m++) { const float w = win_at(s.win, m, t); v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
 #pragma unroll
         for (int j = 0; j < KEEP; j++) raw[j] = raw[j + SH];
 
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
     __syncthreads();                // tables + mbarrier init visible
 #pragma unroll
-    for (int m = 0; m < 16; m++) win[m] = s.win[m * 256 + t];
+    for (int m = 0; m < 16; m++) win[m] = win_at(s.win, m, t);
 
     for (int pr = 0; pr < npairs; pr++) {
         const int off0 = pr * 2 * H;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         // registers for the next pair's analysis window (not live across the transforms)
 #pragma unroll
         for (int m = 0; m < 16; m++) {
-            win[m] = s.win[m * 256 + t];
+            win[m] = win_at(s.win, m, t);
             acc[m] = fmaf(v[m].x, win[m], acc[m]);
             acc[m + HS] = fmaf(v[m].y, win[m], acc[m + HS]);
         }
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
 
 #pragma unroll
         for (int m = 0; m < 16; m++) {
-            const float w = s.win[m * 256 + t];
+            const float w = win_at(s.win, m, t);
             acc[m] = fmaf(v[m].x, w, acc[m]);
             acc[m + HS] = fmaf(v[m].y, w, acc[m + HS]);
         }
