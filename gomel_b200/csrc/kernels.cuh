@@ -511,6 +511,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                 }
                 __syncwarp();
             }
+            float2 nlo[8], nhi[8];               // results go to fresh registers: no in-place ordering constraints
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float ma = mA[j * 256];
@@ -519,9 +520,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                 const float2 z = v[j];
                 const float2 ya = subst_phase(split_a(z, P), ma);
                 const float2 yb = subst_phase(split_b(z, P), mb);
-                v[j] = join_lo(ya, yb);
-                v[15 - j] = shfl2(join_hi(ya, yb), L.src);
+                nlo[j] = join_lo(ya, yb);
+                nhi[j] = shfl2(join_hi(ya, yb), L.src);
             }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { v[j] = nlo[j]; v[15 - j] = nhi[j]; }
             if (w0) {
                 const int j = t - 1;                                   // lanes 1..9 -> special pair j = 0..8
                 if (j >= 0 && j <= 8) {
