@@ -377,6 +377,7 @@ def run_timesplit(args):
     idx = (np.arange(s.frame_begin, s.frame_begin + s.n_frames) % base_frames)
     s.load(base_mel[idx].reshape(-1, 2), None, seed=9001)
     exchange = timesplit.NcclExchange(s) if use_dist else (lambda it: None)
+    native = timesplit.NativeNccl(s) if (args.ts_exchange == "native") else None
 
     def barrier():
         s.sync()
@@ -384,24 +385,26 @@ def run_timesplit(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    it = 0
-    for _ in range(args.warmup):
+    def one_step(it):
+        if native is not None:
+            native.run(it, GL_ITERS, overlap=args.ts_overlap)
+            return it + GL_ITERS
         for _ in range(GL_ITERS):
             if args.ts_overlap:
                 s.iterate(it, 1); exchange(it); s.iterate(it, 2)
             else:
                 s.iterate(it, 0); exchange(it)
             it += 1
+        return it
+
+    it = 0
+    for _ in range(args.warmup):
+        it = one_step(it)
     barrier()
     launches0 = ctx.launch_count()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for _ in range(GL_ITERS):
-            if args.ts_overlap:
-                s.iterate(it, 1); exchange(it); s.iterate(it, 2)
-            else:
-                s.iterate(it, 0); exchange(it)
-            it += 1
+        it = one_step(it)
     s.sync()
     ms = (time.perf_counter() - t0) * 1e3
     barrier()
@@ -422,7 +425,7 @@ def run_timesplit(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[4]: one {args.seconds:.0f} s 44.1 kHz clip ({frames_total} frames), Griffin-Lim "
                                    f"{GL_ITERS} it, frames split by time over {world} GPU(s), NCCL exchange of two 2816-float "
-                                   f"partials per boundary per iteration, tile {args.ts_tile} frames, overlap={bool(args.ts_overlap)}",
+                                   f"partials per boundary per iteration ({args.ts_exchange} NCCL), tile {args.ts_tile} frames, overlap={bool(args.ts_overlap)}",
                        "timing": "host wall clock around stream-synchronised region, max over ranks"},
             "frame_iterations_per_s": fi, "hbm_frac_whole_job": fi * BYTES_PER_FRAME_ITER / 1e9 / (peak * world),
             "gpu_launches": int(launches)}))
@@ -509,6 +512,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
     ap.add_argument("--ts-tile", type=int, default=16, help="timesplit: frames per tile")
     ap.add_argument("--no-ts-overlap", dest="ts_overlap", action="store_false")
+    ap.add_argument("--ts-exchange", default="native", choices=["native", "torch"],
+                    help="timesplit: NCCL called by the library (dlopen) or through torch.distributed P2P ops")
     args = ap.parse_args()
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps

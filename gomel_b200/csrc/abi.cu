@@ -6,6 +6,7 @@
 #include "kernels_f64.cuh"
 
 #include <cmath>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -971,6 +972,7 @@ int gomel_to_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float
 }  // extern "C"
 
 // ------------------------------------------------------------------- time-split Griffin-Lim (config 5)
+static int (*g_nccl_destroy)(void*) = nullptr;      // set once NCCL has been loaded
 struct gomel_ts {
     gomel_ctx* ctx = nullptr;
     gomel_config cfg;
@@ -982,6 +984,7 @@ struct gomel_ts {
     cudaStream_t st_edge = nullptr, st_comm = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_int = nullptr, ev_comm = nullptr;
     bool have_edge = false, have_int = false, have_comm = false;
+    void* nccl_comm = nullptr;
 };
 
 extern "C" {
@@ -1037,6 +1040,7 @@ void gomel_ts_destroy(gomel_ts* ts)
     cudaStreamSynchronize(ts->ctx->st);
     if (ts->st_edge) cudaStreamSynchronize(ts->st_edge);
     if (ts->st_comm) cudaStreamSynchronize(ts->st_comm);
+    if (ts->nccl_comm && g_nccl_destroy) g_nccl_destroy(ts->nccl_comm);
     for (int i = 0; i < 2; i++) { cudaFree(ts->sig[i]); cudaFree(ts->hb[i]); }
     cudaFree(ts->mags);
     if (ts->ev_edge) cudaEventDestroy(ts->ev_edge);
@@ -1195,6 +1199,118 @@ int gomel_copy_d2d(gomel_ctx* ctx, void* dst, const void* src, size_t bytes, voi
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : ctx->st));
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------- in-library NCCL exchange (dlopen)
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, char[128], int) = nullptr;      // ncclUniqueId is passed by value (128 bytes)
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+struct NcclId { char b[128]; };
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool load_nccl(std::string& err)
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.ok) return true;
+    const char* env = getenv("GOMEL_NCCL_LIB");
+    const char* names[3] = { env, "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) {
+        if (!n) continue;
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) { err = "cannot dlopen libnccl.so.2 (set GOMEL_NCCL_LIB)"; return false; }
+    auto sym = [&](const char* n) { return dlsym(g_nccl.handle, n); };
+    g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, char[128], int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+        err = "libnccl is missing a required symbol";
+        return false;
+    }
+    g_nccl_destroy = g_nccl.CommDestroy;
+    g_nccl.ok = true;
+    return true;
+}
+// ncclCommInitRank(ncclComm_t*, int nranks, ncclUniqueId commId /* by value */, int rank)
+typedef int (*comm_init_fn)(void**, int, NcclId, int);
+}  // namespace
+
+extern "C" {
+
+int gomel_nccl_unique_id(gomel_ctx* ctx, char id_out[128])
+{
+    if (!ctx || !id_out) return GOMEL_E_ARG;
+    Guard g(ctx);
+    std::string err;
+    if (!load_nccl(err)) return fail(ctx, GOMEL_E_STATE, err);
+    NcclId id;
+    memset(&id, 0, sizeof id);
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return fail(ctx, GOMEL_E_CUDA, std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    memcpy(id_out, id.b, 128);
+    return 0;
+}
+
+int gomel_ts_nccl_init(gomel_ts* ts, const char id[128])
+{
+    if (!ts || !id) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    std::string err;
+    if (!load_nccl(err)) return fail(ctx, GOMEL_E_STATE, err);
+    if (ts->nccl_comm) return 0;
+    NcclId nid;
+    memcpy(nid.b, id, 128);
+    const int rc = ((comm_init_fn)(void*)g_nccl.CommInitRank)(&ts->nccl_comm, ts->world, nid, ts->rank);
+    if (rc) return fail(ctx, GOMEL_E_CUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return 0;
+}
+
+int gomel_ts_run_nccl(gomel_ts* ts, int first_iter, int n_iters, int overlap)
+{
+    if (!ts || first_iter < 0 || n_iters < 0) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    if (ts->world > 1 && !ts->nccl_comm) { Guard g(ctx); return fail(ctx, GOMEL_E_STATE, "gomel_ts_nccl_init has not been called"); }
+    for (int it = first_iter; it < first_iter + n_iters; it++) {
+        if (int rc = gomel_ts_iterate(ts, it, overlap ? 1 : 0)) return rc;
+        {
+            Guard g(ctx);
+            if (ts->have_edge) CU(cudaStreamWaitEvent(ts->st_comm, ts->ev_edge, 0));
+            float *send_tail, *send_head, *recv_tail, *recv_head;
+            gomel_ts_halo_ptrs(ts, it, &send_tail, &send_head, &recv_tail, &recv_head);
+            if (ts->world > 1) {
+                int rc = g_nccl.GroupStart();
+                if (!rc && send_head) rc = g_nccl.Send(send_head, kHalo, 7 /* ncclFloat */, ts->rank - 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && recv_tail) rc = g_nccl.Recv(recv_tail, kHalo, 7, ts->rank - 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && send_tail) rc = g_nccl.Send(send_tail, kHalo, 7, ts->rank + 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && recv_head) rc = g_nccl.Recv(recv_head, kHalo, 7, ts->rank + 1, ts->nccl_comm, ts->st_comm);
+                const int rc2 = g_nccl.GroupEnd();
+                if (rc || rc2) return fail(ctx, GOMEL_E_CUDA, std::string("NCCL halo exchange: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc ? rc : rc2) : "error"));
+            }
+            CU(cudaEventRecord(ts->ev_comm, ts->st_comm)); ts->have_comm = true;
+        }
+        if (overlap) { if (int rc = gomel_ts_iterate(ts, it, 2)) return rc; }
+    }
     return 0;
 }
 

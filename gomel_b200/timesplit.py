@@ -118,14 +118,15 @@ class NcclExchange:
         import torch.distributed as dist
         self.torch, self.dist, self.s, self.group = torch, dist, session, group
         self.stream = torch.cuda.ExternalStream(session.comm_stream, device=torch.device("cuda", session.ctx.device))
+        self._cache = {}
 
-    def __call__(self, it):
-        torch, dist, s = self.torch, self.dist, self.s
-        p = s.halo_ptrs(it)
-        dev = torch.device("cuda", s.ctx.device)
-        t = lambda ptr: torch.as_tensor(_DevArray(ptr, HALO), device=dev)
-        s.comm_begin(it)
-        with torch.cuda.stream(self.stream):
+    def _ops(self, parity):
+        """P2P op list for iterations of this parity (the four halo pointers alternate between two buffer sets)"""
+        if parity not in self._cache:
+            torch, dist, s = self.torch, self.dist, self.s
+            p = s.halo_ptrs(parity)
+            dev = torch.device("cuda", s.ctx.device)
+            t = lambda ptr: torch.as_tensor(_DevArray(ptr, HALO), device=dev)
             ops = []
             if p["send_head"]:          # previous rank exists
                 ops.append(dist.P2POp(dist.isend, t(p["send_head"]), s.rank - 1, self.group))
@@ -133,10 +134,41 @@ class NcclExchange:
             if p["send_tail"]:          # next rank exists
                 ops.append(dist.P2POp(dist.isend, t(p["send_tail"]), s.rank + 1, self.group))
                 ops.append(dist.P2POp(dist.irecv, t(p["recv_head"]), s.rank + 1, self.group))
-            if ops:
-                for r in dist.batch_isend_irecv(ops):
+            self._cache[parity] = ops
+        return self._cache[parity]
+
+    def __call__(self, it):
+        s = self.s
+        ops = self._ops(it & 1)
+        s.comm_begin(it)
+        if ops:
+            with self.torch.cuda.stream(self.stream):
+                for r in self.dist.batch_isend_irecv(ops):
                     r.wait()            # stream-level wait: the comm stream waits for NCCL, the host does not
         s.comm_end(it)
+
+
+class NativeNccl:
+    """In-library exchange: the library dlopen()s NCCL, builds its own communicator from an id that is
+    distributed here with torch.distributed (any backend), and runs whole iterations without returning to
+    Python (gomel_ts_run_nccl)."""
+
+    def __init__(self, session, group=None):
+        import torch
+        import torch.distributed as dist
+        s = self.s = session
+        ident = C.create_string_buffer(128)
+        if s.world > 1:
+            if s.rank == 0:
+                s.ctx.check(s.ctx.lib.gomel_nccl_unique_id(s.ctx.h, ident))
+            dev = torch.device("cuda", s.ctx.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(ident.raw), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0, group=group)
+            ident = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
+            s.ctx.check(s.ctx.lib.gomel_ts_nccl_init(s.h, ident))
+
+    def run(self, first_iter, n_iters, overlap=True):
+        self.s.ctx.check(self.s.ctx.lib.gomel_ts_run_nccl(self.s.h, first_iter, n_iters, int(overlap)))
 
 
 def run(session, iters, exchange, overlap=True):

@@ -179,6 +179,14 @@ int  gomel_ts_comm_end(gomel_ts *ts, int iter);            /* marks the exchange
 int  gomel_ts_finish(gomel_ts *ts, int iters, float *d_out_local);
 int  gomel_ts_sync(gomel_ts *ts);                          /* host waits for all three streams of the session */
 int  gomel_copy_d2d(gomel_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream /* NULL = ctx stream */);
+/* Optional in-library exchange: NCCL is dlopen()ed (libnccl.so.2 or $GOMEL_NCCL_LIB), the communicator is built
+ * from a 128-byte ncclUniqueId the caller distributes (rank 0 creates it, every rank passes the same bytes), and
+ * gomel_ts_run_nccl enqueues `n_iters` complete iterations -- boundary tiles, ncclSend/ncclRecv of the two
+ * 2816-float partials per neighbour on the communication stream, interior tiles -- without returning to the
+ * caller in between (no per-iteration host work beyond the launches). */
+int  gomel_nccl_unique_id(gomel_ctx *ctx, char id_out[128]);
+int  gomel_ts_nccl_init(gomel_ts *ts, const char id[128]);
+int  gomel_ts_run_nccl(gomel_ts *ts, int first_iter, int n_iters, int overlap);
 
 /* ---- pipelined host batch (end-to-end: pinned host float32 in, float32 out, H2D/compute/D2H
  * overlapped chunk by chunk on three streams).  mel: [n_clips][n_frames*n_mels*2],

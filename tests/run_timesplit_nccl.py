@@ -36,10 +36,13 @@ def main():
     ola = 4096 + (frames - 1) * 1280
     init = np.random.default_rng(9).random(ola).astype(np.float32)
     ok = True
-    for overlap in (False, True):
+    for overlap, native in ((False, False), (True, False), (True, True), (False, True)):
         s = timesplit.Session(ctx, cfg, frames, rank, world, tile)
         s.load(mel[s.frame_begin * 192:(s.frame_begin + s.n_frames) * 192], init[s.sample_begin:s.sample_begin + s.n_samples])
-        timesplit.run(s, iters, timesplit.NcclExchange(s), overlap=overlap)
+        if native:          # library-owned NCCL communicator, whole loop enqueued by one C call
+            timesplit.NativeNccl(s).run(0, iters, overlap=overlap)
+        else:               # torch.distributed P2P ops on the library's communication stream
+            timesplit.run(s, iters, timesplit.NcclExchange(s), overlap=overlap)
         mine = torch.from_numpy(np.ascontiguousarray(s.owned(s.finish(iters)))).cuda()
         lens = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(lens, torch.tensor([mine.numel()], dtype=torch.int64, device="cuda"))
@@ -57,7 +60,7 @@ def main():
             ref = O.from_mel(O.config(gl_iters=iters), mel.astype(np.float64), init.astype(np.float64))
             same = np.array_equal(split.astype(np.float64), whole)
             err = rel_l2(split, ref)
-            print(f"timesplit world={world} overlap={overlap}: bit-identical to unsplit = {same}, rel-L2 vs oracle = {err:.3e}")
+            print(f"timesplit world={world} overlap={overlap} native_nccl={native}: bit-identical to unsplit = {same}, rel-L2 vs oracle = {err:.3e}")
             ok = ok and same and err < 1e-4 and len(split) == ola
         else:
             dist.send(mine, 0)
