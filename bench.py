@@ -373,6 +373,16 @@ def run_timesplit(args):
     ctx.check(ctx.lib.gomel_to_mel_batch_host(ctx.h, C.byref(cfg), wav.ctypes.data_as(C.c_void_p), 1, base_n,
                                               base_mel.ctypes.data_as(C.c_void_p), 1))
     base_mel = base_mel.reshape(base_frames, N_MELS * 2)
+    if args.ts_tile <= 0:
+        # frames per tile: fill whole waves of 2 CTAs/SM (296 CTAs) with this rank's tiles, small tiles preferred
+        per_rank = (frames_total + world - 1) // world
+        best = (0.0, 16)
+        for T in range(12, 34, 2):
+            tiles = (per_rank + T - 1) // T
+            eff = tiles / (((tiles + 295) // 296) * 296.0) - 0.002 * abs(T - 16)
+            if eff > best[0]:
+                best = (eff, T)
+        args.ts_tile = best[1]
     s = timesplit.Session(ctx, cfg, frames_total, rank, world, args.ts_tile)
     idx = (np.arange(s.frame_begin, s.frame_begin + s.n_frames) % base_frames)
     s.load(base_mel[idx].reshape(-1, 2), None, seed=9001)
@@ -510,7 +520,7 @@ def main():
     ap.add_argument("--tile", type=int, default=0, help="frames per tile (0 = library heuristic)")
     ap.add_argument("--workload", default="clips", choices=["clips", "timesplit"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
-    ap.add_argument("--ts-tile", type=int, default=16, help="timesplit: frames per tile")
+    ap.add_argument("--ts-tile", type=int, default=0, help="timesplit: frames per tile (0 = fill whole waves)")
     ap.add_argument("--no-ts-overlap", dest="ts_overlap", action="store_false")
     ap.add_argument("--ts-exchange", default="native", choices=["native", "torch"],
                     help="timesplit: NCCL called by the library (dlopen) or through torch.distributed P2P ops")
