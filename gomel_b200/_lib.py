@@ -8,7 +8,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgomelcuda.so")
+LIB_PATH = os.environ.get("GOMEL_CUDA_LIB") or os.path.join(_HERE, "libgomelcuda.so")   # override: A/B builds
 
 OK, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = 0, -1, -2, -3, -4, -5
 Q_SINGLE_MINMAX, Q_HDR, Q_BLUE_WRAP = 1, 2, 4

@@ -130,26 +130,17 @@ void build_fft_tables(std::vector<float>& blob)
     float* win = T2 + kT2Cells * 2;
     const double two_pi = 6.283185307179586476925286766559;
     auto put = [](float* T, int cell, double a) { T[cell * 2 + 0] = (float)std::cos(a); T[cell * 2 + 1] = (float)(-std::sin(a)); };
-    const int pw[4] = { 1, 2, 4, 8 };
-    // power tables: per lane (w^1, w^2) in float4 row 0 and (w^4, w^8) in row 1; full tables: T[(k>>1)][lane][k&1]
-    if (kPowTwiddles) {
-        for (int i = 0; i < 4; i++)
-            for (int t = 0; t < 256; t++)
-                put(T1, ((i >> 1) * 256 + t) * 2 + (i & 1), two_pi * (double)((t * pw[i]) % 4096) / 4096.0);
-    } else {
-        for (int k0 = 0; k0 < 16; k0++)
-            for (int t = 0; t < 256; t++)
-                put(T1, ((k0 >> 1) * 256 + t) * 2 + (k0 & 1), two_pi * (double)((t * k0) % 4096) / 4096.0);
-    }
-    if (kPowT2) {
-        for (int i = 0; i < 4; i++)
-            for (int n0 = 0; n0 < 16; n0++)
-                put(T2, ((i >> 1) * 16 + n0) * 2 + (i & 1), two_pi * (double)((n0 * pw[i]) % 256) / 256.0);
-    } else {
-        for (int k1 = 0; k1 < 16; k1++)
-            for (int n0 = 0; n0 < 16; n0++)
-                put(T2, ((k1 >> 1) * 16 + n0) * 2 + (k1 & 1), two_pi * (double)((n0 * k1) % 256) / 256.0);
-    }
+    // cell index of power-slot i for a lane: float4 row i>>1, half i&1
+    auto fill = [&](float* T, int mode, int lanes, int period) {
+        for (int i = 0; i < mode; i++) {
+            // mode 4: powers 1,2,4,8 ; mode 8: powers 1..8 ; mode 16: powers 0..15
+            const int pw = mode == 4 ? (1 << i) : (mode == 8 ? i + 1 : i);
+            for (int l = 0; l < lanes; l++)
+                put(T, ((i >> 1) * lanes + l) * 2 + (i & 1), two_pi * (double)((l * pw) % period) / (double)period);
+        }
+    };
+    fill(T1, kT1Mode, 256, 4096);
+    fill(T2, kT2Mode, 16, 256);
     // symmetric Hann of gossp/go-dsp: 0.5*(1-cos(2 pi n/(N-1)))  (phase.py:122 np.hanning)
     for (int m = 0; m < 8; m++)                      // first half only: w[n] = w[4095-n]
         for (int t = 0; t < 256; t++) {

@@ -33,16 +33,18 @@ constexpr int kPlane = 16 * kRow;                          // cells per k0 plane
 constexpr int kXchgCells = 16 * kPlane;                    // padded float2 cells
 constexpr int kXchgBytes = kXchgCells * 8;                 // 36,864 B
 // External twiddles are powers of one per-thread root: W4096^(t*k0) = (W4096^t)^k0, W256^(n0*k1) = (W256^n0)^k1.
-// kPowTwiddles: tables hold only the powers 1,2,4,8 (float64-accurate); the other eleven are formed by
-// one to three packed complex multiplies.  Trades 3/4 of the twiddle shared-memory traffic (the most loaded
-// resource of the kernel) and 25 KB of shared memory for 22 packed instructions per twiddle stage.
-constexpr bool kPowTwiddles = true;      // stage-1 twiddles W4096^(t*k0): 32 KB as a full table
-#ifndef GOMEL_POW_T2
-#define GOMEL_POW_T2 1
+// Table modes (per stage): 4 = powers 1,2,4,8 stored, eleven formed by <=3 packed complex multiplies;
+// 8 = powers 1..8 stored, seven formed by one multiply (w^(8+i) = w^8 * w^i); 16 = full table.
+// Fewer stored powers trade shared-memory traffic (and capacity) for packed FP32 instructions.
+#ifndef GOMEL_T1_MODE
+#define GOMEL_T1_MODE 4
 #endif
-constexpr bool kPowT2 = GOMEL_POW_T2;     // stage-2 twiddles W256^(n0*k1): 2 KB as a full table
-constexpr int kT1Cells = (kPowTwiddles ? 4 : 16) * 256;    // [2][t] float4 = (w^1,w^2),(w^4,w^8)  |  [k0/2][t][k0&1]
-constexpr int kT2Cells = (kPowT2 ? 4 : 16) * 16;           // same for W256^n0
+#ifndef GOMEL_T2_MODE
+#define GOMEL_T2_MODE 4
+#endif
+constexpr int kT1Mode = GOMEL_T1_MODE, kT2Mode = GOMEL_T2_MODE;
+constexpr int kT1Cells = kT1Mode * 256;                    // [mode/2][t] float4
+constexpr int kT2Cells = kT2Mode * 16;
 constexpr int kWinCells = 2048;                            // first half of the symmetric Hann window, [m][t], m < 8
 constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 25,088 B (49,152 B with full tables)
 constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 61,952 B
@@ -225,14 +227,14 @@ __device__ __forceinline__ void radix16(float2 (&v)[16])
 }
 
 // external twiddles v[k] *= w^k (forward) or conj(w)^k (inverse), w = this lane's root
-template <bool INV, bool POW>
+template <bool INV, int MODE>
 __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* T, int rowlen, int lane)
 {
     const float4* T4 = reinterpret_cast<const float4*>(T);
-    if (POW) {
-        const float4 a = T4[lane], b = T4[rowlen + lane];
+    auto mul = [](float2 x, float2 y) { return cmul(x, y.x, y.y); };
+    if (MODE == 4) {
+        const float4 a = T4[lane], b = T4[rowlen + lane];          // (w^1, w^2), (w^4, w^8)
         const float2 w1 = make_float2(a.x, a.y), w2 = make_float2(a.z, a.w), w4 = make_float2(b.x, b.y), w8 = make_float2(b.z, b.w);
-        auto mul = [](float2 x, float2 y) { return cmul(x, y.x, y.y); };
         v[1] = cmul_tw<INV>(v[1], w1); v[2] = cmul_tw<INV>(v[2], w2); v[4] = cmul_tw<INV>(v[4], w4); v[8] = cmul_tw<INV>(v[8], w8);
         const float2 w3 = mul(w2, w1);
         v[3] = cmul_tw<INV>(v[3], w3);
@@ -243,6 +245,18 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const float2* T,
         v[10] = cmul_tw<INV>(v[10], mul(w8, w2));
         v[11] = cmul_tw<INV>(v[11], mul(w8, w3));
         v[12] = cmul_tw<INV>(v[12], mul(w8, w4));
+    } else if (MODE == 8) {
+        // rows q = 0..3 hold (w^(2q+1), w^(2q+2)): w^1..w^8
+        float2 w[9];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 a = T4[q * rowlen + lane];
+            w[2 * q + 1] = make_float2(a.x, a.y); w[2 * q + 2] = make_float2(a.z, a.w);
+        }
+#pragma unroll
+        for (int k = 1; k <= 8; k++) v[k] = cmul_tw<INV>(v[k], w[k]);
+#pragma unroll
+        for (int k = 1; k <= 7; k++) v[8 + k] = cmul_tw<INV>(v[8 + k], mul(w[8], w[k]));
     } else {
         // T[(k>>1)][lane][k&1]: two twiddles per 128-bit shared-memory load
 #pragma unroll
@@ -277,14 +291,14 @@ __device__ __forceinline__ void store_c(const float2 (&v)[16], float2* xb, int b
 __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<false>(v);                                               // n2 -> k0
-    apply_twiddles<false, kPowTwiddles>(v, s.T1, 256, L.t);                        // W4096^(t*k0)
+    apply_twiddles<false, kT1Mode>(v, s.T1, 256, L.t);                        // W4096^(t*k0)
 #pragma unroll
     for (int k0 = 0; k0 < 16; k0++) s.xb[k0 * kPlane + L.base_a] = v[k0];    // pattern (a)
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];           // pattern (b)
     radix16<false>(v);                                               // n1 -> k1
-    apply_twiddles<false, kPowT2>(v, s.T2, 16, L.n0b);                       // W256^(n0*k1)
+    apply_twiddles<false, kT2Mode>(v, s.T2, 16, L.n0b);                       // W256^(n0*k1)
 #pragma unroll
     for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];           // pattern (b), in place
     __syncwarp();                                                    // plane k0 is private to this half-warp
@@ -298,7 +312,7 @@ __device__ __forceinline__ void fft4096_fwd(float2 (&v)[16], const Smem& s, cons
 __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<true>(v);                                                // k2 -> n0
-    apply_twiddles<true, kPowT2>(v, s.T2, 16, L.k1c);                        // conj W256^(n0*k1), table is symmetric
+    apply_twiddles<true, kT2Mode>(v, s.T2, 16, L.k1c);                        // conj W256^(n0*k1), table is symmetric
     store_c(v, s.xb, L.base_c);                                              // pattern (c), in place
     __syncwarp();                                                    // plane k0 is private to this half-warp
 #pragma unroll
@@ -309,7 +323,7 @@ __device__ __forceinline__ void fft4096_inv(float2 (&v)[16], const Smem& s, cons
     __syncthreads();
 #pragma unroll
     for (int k0 = 0; k0 < 16; k0++) v[k0] = s.xb[k0 * kPlane + L.base_a];    // pattern (a)
-    apply_twiddles<true, kPowTwiddles>(v, s.T1, 256, L.t);                         // conj W4096^(t*k0)
+    apply_twiddles<true, kT1Mode>(v, s.T1, 256, L.t);                         // conj W4096^(t*k0)
     radix16<true>(v);                                                // k0 -> n2
 }
 
