@@ -152,7 +152,7 @@ void build_fft_tables(std::vector<float>& blob)
 template <typename K>
 int set_smem_attr(gomel_ctx* ctx, K kernel)
 {
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
     return 0;
 }
 
@@ -229,9 +229,9 @@ int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_si
     const long grid = (long)n_clips * p.tl.n_tiles;
     if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
     CU(cudaEventRecord(ctx->ev_k0, ctx->st));
-    if (mode == MODE_MEL) k_stft_fwd<kHS, MODE_MEL><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
-    else if (mode == MODE_PHASE) k_stft_fwd<kHS, MODE_PHASE><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
-    else k_stft_fwd<kHS, MODE_SPEC><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+    if (mode == MODE_MEL) k_stft_fwd<kHS, MODE_MEL><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
+    else if (mode == MODE_PHASE) k_stft_fwd<kHS, MODE_PHASE><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
+    else k_stft_fwd<kHS, MODE_SPEC><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
     CU(cudaEventRecord(ctx->ev_k1, ctx->st));
     ctx->hot_launches = 1;
     ctx->launches++;
@@ -342,7 +342,7 @@ int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_
     p.hb_out = (float*)hb;
     const long grid = (long)n_clips * p.tl.n_tiles;
     if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
-    k_istft_phase<kHS><<<(unsigned)grid, kThreads, kSmemBytes, ctx->st>>>(p);
+    k_istft_phase<kHS><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
     ctx->launches++;
     if (p.tl.n_tiles > 1) {
         const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;

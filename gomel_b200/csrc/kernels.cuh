@@ -118,6 +118,10 @@ __device__ __forceinline__ float2 join_hi(float2 ya, float2 yb) { return __fadd2
 // and gossp STFT.STFT + the (Im,Re) gather + shrink of phase.ToPhase
 // (phase/phase.go:45-66, phase/impl.go:383-391)      [MODE_PHASE]
 enum { MODE_MEL = 0, MODE_PHASE = 1, MODE_SPEC = 2 };
+// The forward / phase-ISTFT kernels stage their spectra through a buffer of their own (not the FFT exchange
+// buffer): the only CTA barriers per frame pair are the transform's one and the staging hand-over.
+constexpr int kStageBytes = 2 * 2176 * 8;                  // two frames x 2048 padded float2 cells
+constexpr int kFwdSmemBytes = kSmemBytes + kStageBytes;
 
 struct FwdParams {
     const float* sig;        // [clips][sig_stride], zero padded per pad()
@@ -200,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
             }
         }
 
-        __syncthreads();     // every thread is done reading the exchange buffer (pattern c)
+        float2* const stg = reinterpret_cast<float2*>(smem_raw + kSmemBytes);
         if (MODE == MODE_MEL) {
-            float* SA = reinterpret_cast<float*>(s.xb);
+            float* SA = reinterpret_cast<float*>(stg);
             float* SB = SA + 2184;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -250,8 +254,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
                 outp[(long)fr * p.n_mels + mel] = make_float2(logf(t0), logf(t1));
             }
         } else if (MODE == MODE_PHASE) {
-            float2* SA = s.xb;
-            float2* SB = s.xb + 2176;
+            float2* SA = stg;
+            float2* SB = stg + 2176;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = L.klow + 256 * j;          // bin k -> entry k-1
@@ -275,8 +279,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
                 outp[o] = (fr ? SB : SA)[e + (e >> 4)];
             }
         } else {
-            float2* SA = s.xb;
-            float2* SB = s.xb + 2176;      // 2049 + 128 pad = 2177 cells > 2176: bin 2048 goes straight out
+            float2* SA = stg;
+            float2* SB = stg + 2176;       // 2049 + 128 pad = 2177 cells > 2176: bin 2048 goes straight out
             float2* outp = p.spec_out + ((long)clip * p.tl.n_frames + fA) * 2049;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
                 outp[fr * 2049 + e] = (fr ? SB : SA)[e + (e >> 4)];
             }
         }
-        __syncthreads();     // epilogue reads done before the next pair's pattern-(a) writes
+        // no barrier here: the staging buffer is rewritten only after the next pair's transform barrier, and the
+        // staging hand-over barrier above already ordered every stage-3 read before the next pattern-(a) write
     }
 }
 
@@ -640,8 +645,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
 
         // stage the two spectrogram rows (contiguous in memory) into the exchange buffer
         const float2* __restrict__ src = p.spec + ((long)clip * p.tl.n_frames + fA) * nfq;
-        float2* SA = s.xb;
-        float2* SB = s.xb + 2176;
+        float2* SA = reinterpret_cast<float2*>(smem_raw + kSmemBytes);
+        float2* SB = SA + 2176;
 #pragma unroll
         for (int i = 0; i < kPre; i++) {
             const int o = t + i * kThreads;
@@ -672,9 +677,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
             }
             v[j] = make_float2((a.x - b.y) * inv_n, (a.y + b.x) * inv_n);
         }
-        __syncthreads();     // staging reads done before the inverse transform reuses the buffer
-
-        fft4096_inv(v, s, L);
+        fft4096_inv(v, s, L);   // (the staging hand-over barrier above also orders the previous pair's pattern-(a) reads
+                                // before this pair's first exchange write)
 
 #pragma unroll
         for (int m = 0; m < 16; m++) {
@@ -686,7 +690,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
         for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
 #pragma unroll
         for (int j = 0; j < KEEP; j++) acc[j] = acc[j + SH];
-        __syncthreads();     // pattern-(a) reads of the inverse done before the next staging writes
     }
 #pragma unroll
     for (int j = 0; j < KEEP; j++) st(npairs * 2 * H + j * 256, acc[j]);
