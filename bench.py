@@ -333,6 +333,17 @@ def run_product(args):
         }
     if args.stft and rank == 0 and line is not None:
         line["stft_side"] = bench_to_mel(ctx, cfg, _lib, args)
+        # configs[3] also names 100 iterations: same batch, same call, GriffinLimIterations = 100
+        cfg100 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=100)
+        call = lambda sd: ctx.check(ctx.lib.gomel_from_mel_dev(ctx.h, C.byref(cfg100), d_mel, clips, frames, None, sd, ola, d_out))
+        call(1)
+        ctx.sync()
+        ctx.timer_start()
+        call(2)
+        ms100 = ctx.timer_stop()
+        line["gl100"] = {"workload": f"configs[3] with 100 iterations, {clips} clips, device-resident", "ms_per_step": ms100,
+                         "audio_s_per_s": clips * frames * HOP / SR / (ms100 / 1e3),
+                         "frame_iterations_per_s": clips * frames * 100 / (ms100 / 1e3)}
     ctx.dev_free(d_mel)
     ctx.dev_free(d_out)
     ctx.host_free(h_mel_owner)

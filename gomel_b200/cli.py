@@ -5,6 +5,8 @@
     python -m gomel_b200.cli towav  file.png [rate]   -> file.png.wav      (cmd/towav/main.go:27-44)
     python -m gomel_b200.cli tophase file.wav         -> file.wav.png      (cmd/tophase/main.go:21-55)
     python -m gomel_b200.cli fromphase file.png       -> file.png.wav      (cmd/fromphase/main.go:20-32)
+    python -m gomel_b200.cli tomel-dir  in_dir out_dir   every *.wav in one batched GPU call (gomel_b200/batch.py)
+    python -m gomel_b200.cli towav-dir  in_dir out_dir   every *.png, grouped by frame count
 """
 import sys
 
@@ -35,6 +37,12 @@ def main(argv=None):
             if len(argv) > 2:
                 m.SampleRate = int(argv[2])
             m.ToWavPng(name, name + ".wav")
+        elif tool == "tomel-dir":
+            from . import batch
+            print("\n".join(batch.tomel_dir(name, argv[2], _mel())))
+        elif tool == "towav-dir":
+            from . import batch
+            print("\n".join(batch.towav_dir(name, argv[2], _mel())))
         elif tool == "tophase":
             Phase().to_phase_wav(name, name + ".png")
         elif tool == "fromphase":
