@@ -470,3 +470,48 @@ def test_fp32_deviation_is_the_algorithms_conditioning(mctx, oracle):
         assert dev < 200 * sens                  # 32 iterations x several roundings each, same amplification
         if must_pass:
             assert dev < TOL_GL
+
+
+# ------------------------------------------------------------------ small / unusual inputs of the buffer API
+@pytest.mark.parametrize("frames", [1, 2, 3, 5, 8])
+def test_from_mel_tiny_frame_counts(mctx, oracle, frames):
+    """FromMel accepts any number of frames (the PNG path feeds it whatever the image width is)"""
+    rng = np.random.default_rng(frames)
+    mel = rng.uniform(-9.0, 3.0, (frames * 192, 2))
+    init = rng.random(4096 + (frames - 1) * 1280)
+    m = _mel_obj(3, False)
+    m.InitSignal = init
+    got = m.FromMel(mel.copy())
+    ref = oracle.from_mel(oracle.config(gl_iters=3), mel, init)
+    assert got.shape == ref.shape and rel_l2(got, ref) < TOL_GL
+
+
+def test_from_mel_tune_parameters(mctx, oracle):
+    """TuneMul / TuneAdd of Mel.undospectrum (mel/impl.go:386-408), incl. the Abs() of a negative result"""
+    mel = oracle.to_mel(oracle.config(), synth_clip(16, 0.4))
+    frames = len(mel) // 192
+    init = np.random.default_rng(3).random(4096 + (frames - 1) * 1280)
+    m = _mel_obj(2, False)
+    m.TuneMul, m.TuneAdd = 2.5, 0.75
+    m.InitSignal = init
+    got = m.FromMel(mel.copy())
+    ref = oracle.from_mel(oracle.config(gl_iters=2, tune_mul=2.5, tune_add=0.75), mel, init)
+    assert rel_l2(got, ref) < TOL_GL
+
+
+def test_other_mel_counts(mctx, lib, oracle):
+    """NumMels other than 192 (cmd/tomel uses 192, NewMel's default is 160)"""
+    from gomel_b200 import NewMel
+    wav = synth_clip(17, 0.5)
+    for mels, fmax in ((160, 8000.0), (80, 16000.0), (256, 16000.0)):
+        m = NewMel()
+        m.NumMels, m.MelFmin, m.MelFmax, m.Window, m.Resolut, m.GriffinLimIterations = mels, 0.0, fmax, 1280, 4096, 2
+        ocfg = oracle.config(num_mels=mels, mel_fmax=fmax, gl_iters=2)
+        mel = m.ToMel(wav)
+        ref = oracle.to_mel(ocfg, wav)
+        assert mel.shape == ref.shape and rel_l2(np.exp(mel), np.exp(ref)) < TOL_STFT
+        frames = len(ref) // mels
+        init = np.random.default_rng(mels).random(4096 + (frames - 1) * 1280)
+        m.InitSignal = init
+        assert rel_l2(m.FromMel(ref.copy()), oracle.from_mel(ocfg, ref, init)) < TOL_GL
+    mctx.set_mel_tables(mel_cfg(lib), 0.0, 16000.0)            # restore the module fixture's tables
