@@ -193,7 +193,7 @@ def workload_config(n_gpus):
 # ------------------------------------------------------------------------------- product arm
 def run_product(args):
     rank, local_rank, world = dist_env()
-    n_gpus = args.gpus
+    n_gpus = world                      # one process per GPU; --gpus is informational when launched by torchrun
     use_dist = world > 1
     if use_dist:
         import torch

@@ -21,7 +21,7 @@ constexpr int kHS = 5;                       // hop slots: Window / 256 = 1280 /
 constexpr int kHop = 256 * kHS;
 constexpr int kHalo = (16 - kHS) * 256;      // Resolut - Window = 2816 samples shared by adjacent tiles
 
-enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_F32C, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
+enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
                S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_COUNT };
 
 }  // namespace

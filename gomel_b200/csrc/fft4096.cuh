@@ -46,13 +46,13 @@ constexpr int kT1Mode = GOMEL_T1_MODE, kT2Mode = GOMEL_T2_MODE;
 constexpr int kT1Cells = kT1Mode * 256;                    // [mode/2][t] float4
 constexpr int kT2Cells = kT2Mode * 16;
 constexpr int kWinCells = 2048;                            // first half of the symmetric Hann window, [m][t], m < 8
-constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 25,088 B (49,152 B with full tables)
-constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 61,952 B
+constexpr int kTableBytes = kT1Cells * 8 + kT2Cells * 8 + kWinCells * 4;   // 16,896 B in the default 4/4 mode
+constexpr int kSmemBytes = kTableBytes + kXchgBytes;       // 53,760 B
 
 struct Smem {
-    float2* T1;     // [15][256]
-    float2* T2;     // [16][16]
-    float*  win;    // [16][256]
+    float2* T1;     // stage-1 roots W4096^t: [kT1Mode/2][256] float4 (two powers per cell)
+    float2* T2;     // stage-2 roots W256^n0: [kT2Mode/2][16] float4
+    float*  win;    // first half of the Hann window, [8][256]
     float2* xb;     // exchange buffer, kXchgCells
 };
 
@@ -83,7 +83,7 @@ __device__ __forceinline__ void load_tables(const Smem& s, const float4* __restr
 
 // per-thread indices for the three exchange patterns and the spectrum layout
 struct Lanes {
-    int t;         // thread id; pattern (a): cell k0*272 + base_a
+    int t;         // thread id
     int base_a;    // t + 2*(t>>4); slot k0: + k0*kPlane
     int base_b;    // pattern (b): thread (k0b,n0b), slot r: base_b + r*kRow.  k0b == k0c: the 16 threads that share a
                    // k0 plane form the same half-warp in stages 2 and 3, so the exchange between those stages is warp-local

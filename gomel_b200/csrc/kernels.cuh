@@ -74,12 +74,6 @@ __global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ 
     const long step = (long)gridDim.x * blockDim.x;
     for (; i < n; i += step) out[i] = (double)in[i] * scale;
 }
-__global__ void k_fill_f32(float* __restrict__ out, long n, float v)
-{
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long step = (long)gridDim.x * blockDim.x;
-    for (; i < n; i += step) out[i] = v;
-}
 // counter-based U[0,1) fill for the Griffin-Lim start signal when the caller injects none
 // (mel/mel.go:80-83 draws rand.Float64(); same distribution, not bit-compatible with math/rand)
 __global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long long seed, long index_offset = 0)
@@ -349,7 +343,6 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
 }
 
 // ------------------------------------------------------------------ shared pieces of the synthesis kernels
-constexpr int kMaxHalo = 15 * 256;
 
 struct SynParams {
     const float4* tables;
