@@ -385,16 +385,17 @@ def run_timesplit(args):
                                               base_mel.ctypes.data_as(C.c_void_p), 1))
     base_mel = base_mel.reshape(base_frames, N_MELS * 2)
     if args.ts_tile <= 0:
-        # frames per tile: fill whole waves of 2 CTAs/SM (296 CTAs) with this rank's tiles, small tiles preferred
+        # frames per interior tile: fill whole waves of 2 CTAs/SM (296 CTAs) with this rank's tiles; long tiles
+        # amortise the per-tile prologue, the short boundary tiles (--ts-edge) keep the exchange path short
         per_rank = (frames_total + world - 1) // world
         best = (0.0, 16)
-        for T in range(12, 34, 2):
+        for T in range(16, 122, 2):
             tiles = (per_rank + T - 1) // T
-            eff = tiles / (((tiles + 295) // 296) * 296.0) - 0.002 * abs(T - 16)
+            eff = tiles / (((tiles + 295) // 296) * 296.0) + 0.0005 * T
             if eff > best[0]:
                 best = (eff, T)
         args.ts_tile = best[1]
-    s = timesplit.Session(ctx, cfg, frames_total, rank, world, args.ts_tile)
+    s = timesplit.Session(ctx, cfg, frames_total, rank, world, args.ts_tile, args.ts_edge)
     idx = (np.arange(s.frame_begin, s.frame_begin + s.n_frames) % base_frames)
     s.load(base_mel[idx].reshape(-1, 2), None, seed=9001)
     exchange = timesplit.NcclExchange(s) if use_dist else (lambda it: None)
@@ -446,7 +447,7 @@ def run_timesplit(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[4]: one {args.seconds:.0f} s 44.1 kHz clip ({frames_total} frames), Griffin-Lim "
                                    f"{GL_ITERS} it, frames split by time over {world} GPU(s), NCCL exchange of two 2816-float "
-                                   f"partials per boundary per iteration ({args.ts_exchange} NCCL), tile {args.ts_tile} frames, overlap={bool(args.ts_overlap)}",
+                                   f"partials per boundary per iteration ({args.ts_exchange} NCCL), tile {args.ts_tile} frames, boundary tiles {args.ts_edge}, overlap={bool(args.ts_overlap)}",
                        "timing": "host wall clock around stream-synchronised region, max over ranks"},
             "frame_iterations_per_s": fi, "hbm_frac_whole_job": fi * BYTES_PER_FRAME_ITER / 1e9 / (peak * world),
             "gpu_launches": int(launches)}))
@@ -532,6 +533,7 @@ def main():
     ap.add_argument("--workload", default="clips", choices=["clips", "timesplit"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
     ap.add_argument("--ts-tile", type=int, default=0, help="timesplit: frames per tile (0 = fill whole waves)")
+    ap.add_argument("--ts-edge", type=int, default=8, help="timesplit: frames in the tiles next to a rank boundary (0 = uniform)")
     ap.add_argument("--no-ts-overlap", dest="ts_overlap", action="store_false")
     ap.add_argument("--ts-exchange", default="native", choices=["native", "torch"],
                     help="timesplit: NCCL called by the library (dlopen) or through torch.distributed P2P ops")

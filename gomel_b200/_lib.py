@@ -69,6 +69,7 @@ SIGNATURES = {
     "gomel_from_mel_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, C.c_long, _vp]),
     "gomel_from_phase_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, C.c_long, _vp]),
     "gomel_ts_create": (C.c_int, [_vp, _cp, C.c_long, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "gomel_ts_create2": (C.c_int, [_vp, _cp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "gomel_ts_destroy": (None, [_vp]),
     "gomel_ts_range": (C.c_int, [_vp, _lp, _lp, _lp, _lp]),
     "gomel_ts_load": (C.c_int, [_vp, _vp, _vp, C.c_ulonglong]),

@@ -115,6 +115,7 @@ Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, 
     if (T < 4) T = 4;
     tl.tile_frames = T;
     tl.n_tiles = (int)((n_frames + T - 1) / T);
+    tl.edge_first = tl.edge_last = 0;
     tl.sig_stride = sig_stride;
     tl.sig_len = sig_len;
     return tl;
@@ -980,14 +981,15 @@ struct gomel_ts {
 
 extern "C" {
 
-int gomel_ts_create(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_total, int rank, int world,
-                    int tile_frames, gomel_ts** out)
+int gomel_ts_create2(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_total, int rank, int world,
+                     int tile_frames, int edge_frames, gomel_ts** out)
 {
     if (!ctx || !out) return GOMEL_E_ARG;
     Guard g(ctx);
     *out = nullptr;
     if (int rc = check_cfg(ctx, cfg)) return rc;
-    if (world < 1 || rank < 0 || rank >= world || n_frames_total <= 0) return fail(ctx, GOMEL_E_ARG, "bad rank/world/frames");
+    if (world < 1 || rank < 0 || rank >= world || n_frames_total <= 0 || edge_frames < 0)
+        return fail(ctx, GOMEL_E_ARG, "bad rank/world/frames");
     int T = tile_frames > 0 ? tile_frames : 16;
     if (T & 1) T++;
     if (T < 4) T = 4;
@@ -1002,8 +1004,24 @@ int gomel_ts_create(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_total
     ts->sample_begin = ts->f_begin * kHop;
     ts->n_samples = ts->n_local * kHop + kHalo;
     ts->ext_prev = rank > 0; ts->ext_next = rank + 1 < world;
-    ts->tl.n_frames = (int)ts->n_local; ts->tl.tile_frames = T; ts->tl.n_tiles = (int)((ts->n_local + T - 1) / T);
+    ts->tl.n_frames = (int)ts->n_local; ts->tl.tile_frames = T;
     ts->tl.sig_stride = ts->n_samples; ts->tl.sig_len = ts->n_samples;
+    // short tiles next to a rank boundary (the ones the halo exchange waits for); every tile but the clip's last
+    // must hold whole pairs and be at least 4 frames long (>= Resolut - Window samples)
+    int e = edge_frames & ~1;
+    if (e > 0 && e < 4) e = 4;
+    if (e >= T) e = 0;
+    int ef = ts->ext_prev ? e : 0, el = ts->ext_next ? e : 0;
+    auto rem_ok = [&](int ef_, int el_) {
+        const long mid = ts->n_local - ef_ - el_;
+        if (mid < 4) return false;
+        const long r = mid % T;
+        return r == 0 || r >= 4 || !ts->ext_next;      // the remainder tile precedes the short last tile
+    };
+    while ((ef || el) && !rem_ok(ef, el)) { if (el) el = el > 4 ? el - 2 : 0; else ef = ef > 4 ? ef - 2 : 0; }
+    ts->tl.edge_first = ef; ts->tl.edge_last = el;
+    const long mid = ts->n_local - ef - el;
+    ts->tl.n_tiles = (ef > 0) + (int)((mid + T - 1) / T) + (el > 0);
     auto boot = [&]() -> int {
         const size_t hb_bytes = (size_t)(ts->tl.n_tiles + 1) * kHalo * 4;
         for (int i = 0; i < 2; i++) {
@@ -1172,6 +1190,12 @@ int gomel_ts_finish(gomel_ts* ts, int iters, float* d_out_local)
     CU(cudaMemcpyAsync(d_out_local, fin, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return 0;
+}
+
+int gomel_ts_create(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_total, int rank, int world,
+                    int tile_frames, gomel_ts** out)
+{
+    return gomel_ts_create2(ctx, cfg, n_frames_total, rank, world, tile_frames, 0, out);
 }
 
 int gomel_ts_sync(gomel_ts* ts)

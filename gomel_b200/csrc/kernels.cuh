@@ -92,11 +92,23 @@ __global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long lo
 // ------------------------------------------------------------------ tile geometry
 struct Tiling {
     int n_frames;        // frames per clip
-    int tile_frames;     // T, even
-    int n_tiles;         // ceil(n_frames / T)
+    int tile_frames;     // T, even: frames per (interior) tile
+    int n_tiles;         // tiles per clip
     long sig_stride;     // floats between clips in signal buffers
     long sig_len;        // valid samples per clip (loads beyond read as 0, stores beyond dropped)
+    // time-split sessions only: a short first / last tile (even, >= 4 frames; 0 = none) so that the tiles that
+    // wait for a neighbouring rank are cheap while the interior tiles stay long
+    int edge_first, edge_last;
 };
+// first frame of tile `tile` (tile == n_tiles gives n_frames)
+__host__ __device__ __forceinline__ int tile_begin(const Tiling& tl, int tile)
+{
+    if (tile >= tl.n_tiles) return tl.n_frames;
+    if (tl.edge_first > 0) { if (tile == 0) return 0; tile--; }
+    const int b = tl.edge_first + tile * tl.tile_frames;
+    const int last0 = tl.n_frames - tl.edge_last;            // start of the short last tile (== n_frames if none)
+    return b < last0 ? b : last0;
+}
 
 // the two real spectra riding one complex transform, up to a common factor 2 (P = Z[N-k]):
 //   2*XA = Z + conj P ,  2*XB = (Z - conj P)/i
@@ -140,8 +152,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
     load_tables(s, p.tables, L.t);
     constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS;
     const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
-    const int f0 = tile * p.tl.tile_frames;
-    const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
+    const int f0 = tile_begin(p.tl, tile);
+    const int nf = tile_begin(p.tl, tile + 1) - f0;
     const int npairs = (nf + 1) >> 1;
     const float* __restrict__ sig = p.sig + (long)clip * p.tl.sig_stride + (long)f0 * H;
     const long lim = p.tl.sig_len - (long)f0 * H;
@@ -406,10 +418,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     int tile, clip;
     if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
     else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = blockIdx.x / p.tiles_in_launch; }
-    const int f0 = tile * p.tl.tile_frames;
-    const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
+    const int f0 = tile_begin(p.tl, tile);
+    const int nf = tile_begin(p.tl, tile + 1) - f0;
     const int npairs = (nf + 1) >> 1;
-    const int tile_len = p.tl.tile_frames * H;
+    const int tile_len = nf * H;           // this tile's own length (every tile but a clip's last holds whole pairs)
     const long sbase = (long)f0 * H;
     const float* __restrict__ sin_ = p.sig_in + (long)clip * p.tl.sig_stride + sbase;
     float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
@@ -591,10 +603,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     load_tables(s, p.tables, L.t);
     constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
     const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
-    const int f0 = tile * p.tl.tile_frames;
-    const int nf = min(p.tl.tile_frames, p.tl.n_frames - f0);
+    const int f0 = tile_begin(p.tl, tile);
+    const int nf = tile_begin(p.tl, tile + 1) - f0;
     const int npairs = (nf + 1) >> 1;
-    const int tile_len = p.tl.tile_frames * H;
+    const int tile_len = nf * H;
     const long sbase = (long)f0 * H;
     float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
     const long lim = p.tl.sig_len - sbase;
@@ -701,7 +713,7 @@ __global__ void k_halo_fix(float* __restrict__ sig, const float* __restrict__ hb
         const int clip = (int)(i / per_clip);
         const long r = i - (long)clip * per_clip;
         const int tile = (int)(r / halo) + t_first, o = (int)(r % halo);
-        const long s_abs = (long)tile * tl.tile_frames * hop + o;
+        const long s_abs = (long)tile_begin(tl, tile) * hop + o;
         if (s_abs >= tl.sig_len) continue;
         float* d = sig + (long)clip * tl.sig_stride + s_abs;
         float x = *d + hb[((long)clip * hb_tiles + tile) * halo + o];

@@ -36,10 +36,11 @@ def partition(n_frames_total, world, tile_frames=16):
 class Session:
     """gomel_ts: this rank's slice of one clip."""
 
-    def __init__(self, ctx, cfg, n_frames_total, rank, world, tile_frames=16):
+    def __init__(self, ctx, cfg, n_frames_total, rank, world, tile_frames=16, edge_frames=0):
         self.ctx, self.cfg, self.rank, self.world = ctx, cfg, rank, world
         h = C.c_void_p()
-        ctx.check(ctx.lib.gomel_ts_create(ctx.h, C.byref(cfg), n_frames_total, rank, world, tile_frames, C.byref(h)))
+        ctx.check(ctx.lib.gomel_ts_create2(ctx.h, C.byref(cfg), n_frames_total, rank, world, tile_frames, edge_frames,
+                                           C.byref(h)))
         self.h = h
         a, b, c, d = C.c_long(), C.c_long(), C.c_long(), C.c_long()
         ctx.check(ctx.lib.gomel_ts_range(h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
@@ -184,12 +185,12 @@ def run(session, iters, exchange, overlap=True):
             exchange(it)
 
 
-def run_local(ctx, cfg, mel, init, iters, world, tile_frames=16, overlap=False):
+def run_local(ctx, cfg, mel, init, iters, world, tile_frames=16, overlap=False, edge_frames=0):
     """`world` ranks emulated as `world` sessions of ONE process / ONE GPU; the exchange is a
     device-to-device copy.  Returns the stitched float32 signal.  (Multi-rank test on one GPU.)"""
     mel = np.ascontiguousarray(mel, np.float32).reshape(-1, 2)
     n_frames = len(mel) // cfg.n_mels
-    sessions = [Session(ctx, cfg, n_frames, r, world, tile_frames) for r in range(world)]
+    sessions = [Session(ctx, cfg, n_frames, r, world, tile_frames, edge_frames) for r in range(world)]
     try:
         for s in sessions:
             m = mel[s.frame_begin * cfg.n_mels:(s.frame_begin + s.n_frames) * cfg.n_mels]

@@ -163,6 +163,10 @@ int  gomel_from_phase_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *
 typedef struct gomel_ts gomel_ts;
 int  gomel_ts_create(gomel_ctx *ctx, const gomel_config *cfg, long n_frames_total, int rank, int world,
                      int tile_frames, gomel_ts **out);
+/* as gomel_ts_create, plus `edge_frames`: length of the tiles next to a rank boundary (even, >= 4; 0 = uniform
+ * tiles).  Short boundary tiles keep the exchange's critical path short while interior tiles stay long. */
+int  gomel_ts_create2(gomel_ctx *ctx, const gomel_config *cfg, long n_frames_total, int rank, int world,
+                      int tile_frames, int edge_frames, gomel_ts **out);
 void gomel_ts_destroy(gomel_ts *ts);
 /* frames [frame_begin, frame_begin+n_frames_local); local buffers hold global samples
  * [sample_begin, sample_begin+n_samples_local), n_samples_local = n_frames_local*Window + 2816 */

@@ -36,8 +36,8 @@ def main():
     ola = 4096 + (frames - 1) * 1280
     init = np.random.default_rng(9).random(ola).astype(np.float32)
     ok = True
-    for overlap, native in ((False, False), (True, False), (True, True), (False, True)):
-        s = timesplit.Session(ctx, cfg, frames, rank, world, tile)
+    for overlap, native, edge in ((False, False, 0), (True, False, 0), (True, True, 0), (False, True, 0), (True, True, 4)):
+        s = timesplit.Session(ctx, cfg, frames, rank, world, tile if not edge else 12, edge)
         s.load(mel[s.frame_begin * 192:(s.frame_begin + s.n_frames) * 192], init[s.sample_begin:s.sample_begin + s.n_samples])
         if native:          # library-owned NCCL communicator, whole loop enqueued by one C call
             timesplit.NativeNccl(s).run(0, iters, overlap=overlap)
@@ -58,9 +58,11 @@ def main():
             whole = ctx.from_mel(cfg, mel.astype(np.float64), init=init.astype(np.float64))
             ctx.set_tile_frames(0)
             ref = O.from_mel(O.config(gl_iters=iters), mel.astype(np.float64), init.astype(np.float64))
-            same = np.array_equal(split.astype(np.float64), whole)
+            # uniform tiles share their boundaries with the unsplit run -> identical bits; short boundary tiles
+            # change the order of the partial sums -> equal to rounding
+            same = np.array_equal(split.astype(np.float64), whole) if not edge else rel_l2(split, whole) < 2e-6
             err = rel_l2(split, ref)
-            print(f"timesplit world={world} overlap={overlap} native_nccl={native}: bit-identical to unsplit = {same}, rel-L2 vs oracle = {err:.3e}")
+            print(f"timesplit world={world} overlap={overlap} native_nccl={native} edge={edge}: bit-identical to unsplit = {same}, rel-L2 vs oracle = {err:.3e}")
             ok = ok and same and err < 1e-4 and len(split) == ola
         else:
             dist.send(mine, 0)

@@ -327,6 +327,26 @@ def test_timesplit_emulated_ranks_match_single_gpu(mctx, lib, oracle, world, ove
     assert rel_l2(split, ref) < TOL_GL
 
 
+@pytest.mark.parametrize("world,tile,edge", [(2, 12, 4), (3, 10, 6), (2, 30, 8)])
+def test_timesplit_short_boundary_tiles(mctx, lib, oracle, world, tile, edge):
+    """non-uniform tiling (short tiles next to a rank boundary, long interior tiles): same result as the unsplit
+    run up to the order of the partial sums, and inside the Griffin-Lim tolerance of the oracle"""
+    from gomel_b200 import timesplit
+    iters = 3
+    cfg = mel_cfg(lib, iters=iters)
+    mel = oracle.to_mel(oracle.config(), synth_clip(51, 3.3))
+    frames = len(mel) // 192
+    ola = 4096 + (frames - 1) * 1280
+    init = np.random.default_rng(78).random(ola).astype(np.float32)
+    split = timesplit.run_local(mctx, cfg, mel, init, iters, world, tile_frames=tile, overlap=True, edge_frames=edge)
+    mel32 = mel.astype(np.float32).astype(np.float64)
+    whole = mctx.from_mel(cfg, mel32, init=init.astype(np.float64))
+    assert split.shape == (ola,)
+    assert rel_l2(split, whole) < 2e-6
+    ref = oracle.from_mel(oracle.config(gl_iters=iters), mel32, init.astype(np.float64))
+    assert rel_l2(split, ref) < TOL_GL
+
+
 def test_timesplit_real_nccl_when_two_gpus():
     """the NCCL halo exchange itself needs >= 2 GPUs (gpurun --gpus 2); on one GPU the multi-rank
     path is covered by test_timesplit_emulated_ranks_match_single_gpu"""
