@@ -879,14 +879,17 @@ int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const flo
     std::vector<int> sizes;
     {
         int left = n_clips;
+        const char* ef = getenv("GOMEL_CHUNK_TAPER_MIN");           // smallest tapered chunk (tuning knob)
+        int floor_ = ef ? atoi(ef) : 64;
+        if (floor_ < 1) floor_ = 1;
         const int first = cpc >= 128 ? cpc / 4 : cpc;
         auto push = [&](int n) { n = n < left ? n : left; if (n > 0) { sizes.push_back(n); left -= n; } };
         push(first);
         int taper = 0;
-        for (int t = cpc / 2; t >= 16; t /= 2) taper += t;
+        for (int t = cpc / 2; t >= floor_; t /= 2) taper += t;
         while (left > taper + cpc) push(cpc);
         if (left > taper) push(left - taper);
-        for (int t = cpc / 2; t >= 16 && left > 0; t /= 2) push(t);
+        for (int t = cpc / 2; t >= floor_ && left > 0; t /= 2) push(t);
         push(left);
     }
     const int n_chunks = (int)sizes.size();
