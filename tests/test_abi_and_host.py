@@ -146,3 +146,49 @@ def test_reference_fixture_is_the_old_format():
     im = Image.open(p)
     assert im.size == (183, 80)
     assert (183 * 80) % 192 != 0
+
+
+def test_png16_reader_handles_all_filter_types(tmp_path):
+    """Go's png.Encode picks a filter per row; the 16-bit reader (used for HDR images written by the Go reference)
+    must undo all five.  Rows are filtered here by hand, one type per row."""
+    import struct
+    import zlib
+    from gomel_b200 import codec
+    rng = np.random.default_rng(1)
+    h, w, ch = 10, 7, 3
+    px = rng.integers(0, 65535, (h, w, ch)).astype(np.uint16)
+    raw = px.astype(">u2").reshape(h, -1).view(np.uint8).astype(np.int32)       # (h, w*6) bytes
+    bpp = ch * 2
+    out = bytearray()
+    prev = np.zeros(raw.shape[1], np.int32)
+    for y in range(h):
+        ft = y % 5
+        cur = raw[y]
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        b = prev
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        if ft == 0:
+            pred = np.zeros_like(cur)
+        elif ft == 1:
+            pred = a
+        elif ft == 2:
+            pred = b
+        elif ft == 3:
+            pred = (a + b) >> 1
+        else:
+            p = a + b - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+        out.append(ft)
+        out.extend(((cur - pred) & 255).astype(np.uint8).tobytes())
+        prev = cur
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    f = str(tmp_path / "filtered16.png")
+    with open(f, "wb") as fh:
+        fh.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 16, 2, 0, 0, 0))
+                 + chunk(b"IDAT", zlib.compress(bytes(out))) + chunk(b"IEND", b""))
+    back = codec.read_png(f)
+    assert back.dtype == np.uint16 and np.array_equal(back, px)
