@@ -341,6 +341,7 @@ def run_product(args):
         ctx.timer_start()
         call(2)
         ms100 = ctx.timer_stop()
+        line["cufft_comparison"] = bench_cufft_comparison(clips, frames)
         line["gl100"] = {"workload": f"configs[3] with 100 iterations, {clips} clips, device-resident", "ms_per_step": ms100,
                          "audio_s_per_s": clips * frames * HOP / SR / (ms100 / 1e3),
                          "frame_iterations_per_s": clips * frames * 100 / (ms100 / 1e3)}
@@ -455,6 +456,32 @@ def run_timesplit(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bench_cufft_comparison(clips, frames):
+    """Comparison point only (BASELINE north_star): cuFFT batched R2C-4096 + C2R-4096 over the frames of ONE
+    Griffin-Lim iteration (through torch.fft, which calls cuFFT), i.e. just the two transforms as separate
+    library passes -- no framing, window, magnitude substitution or overlap-add.  Not on the product path."""
+    try:
+        import torch
+        x = torch.rand((clips * frames, N_FFT), device="cuda", dtype=torch.float32)
+        for _ in range(2):
+            y = torch.fft.irfft(torch.fft.rfft(x, dim=1), n=N_FFT, dim=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            y = torch.fft.irfft(torch.fft.rfft(x, dim=1), n=N_FFT, dim=1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        del x, y
+        torch.cuda.empty_cache()
+        return {"what": "cuFFT R2C-4096 + C2R-4096 (torch.fft.rfft/irfft), transforms only, separate passes",
+                "frames": clips * frames, "ms": ms, "frame_pairs_of_transforms_per_s": clips * frames / (ms / 1e3)}
+    except Exception as e:      # noqa: BLE001  (comparison point only)
+        return {"unavailable": repr(e)[:200]}
 
 
 def bench_to_mel(ctx, cfg, _lib, args):
