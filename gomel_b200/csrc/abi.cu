@@ -177,7 +177,7 @@ int prepare_gain(gomel_ctx* ctx, long n_frames, double boost)
         if (v > thr) g = 1.0 / v;
         else if (v > 1e-21) g = 1.0 / thr;
         if (boost != 0) g *= boost;
-        return (float)g;
+        return (float)(g / (double)kN);         // includes the 1/N of the inverse transform (fft.IFFT divides by N)
     };
     std::vector<float> head, mid(kHop, 1.0f), tail;
     if (n_frames <= 16) {

@@ -110,6 +110,12 @@ __host__ __device__ __forceinline__ int tile_begin(const Tiling& tl, int tile)
     return b < last0 ? b : last0;
 }
 
+__device__ __forceinline__ float sqrt_fast(float x)        // one MUFU.SQRT (max relative error 2^-23): plenty for 1e-5 parity
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 // the two real spectra riding one complex transform, up to a common factor 2 (P = Z[N-k]):
 //   2*XA = Z + conj P ,  2*XB = (Z - conj P)/i
 __device__ __forceinline__ float2 split_a(float2 z, float2 P) { return __fadd2_rn(z, make_float2(P.x, -P.y)); }
@@ -217,12 +223,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = L.klow + 256 * j, q = k + (k >> 4);
-                SA[q] = sqrtf(xa[j].x * xa[j].x + xa[j].y * xa[j].y);
-                SB[q] = sqrtf(xb[j].x * xb[j].x + xb[j].y * xb[j].y);
+                SA[q] = sqrt_fast(fmaf(xa[j].x, xa[j].x, xa[j].y * xa[j].y));
+                SB[q] = sqrt_fast(fmaf(xb[j].x, xb[j].x, xb[j].y * xb[j].y));
             }
             if (L.special) {
-                SA[2048 + 128] = sqrtf(xa[8].x * xa[8].x + xa[8].y * xa[8].y);
-                SB[2048 + 128] = sqrtf(xb[8].x * xb[8].x + xb[8].y * xb[8].y);
+                SA[2048 + 128] = sqrt_fast(fmaf(xa[8].x, xa[8].x, xa[8].y * xa[8].y));
+                SB[2048 + 128] = sqrt_fast(fmaf(xb[8].x, xb[8].x, xb[8].y * xb[8].y));
             }
             __syncthreads();
             // domel (mel/impl.go:310-345): one work item = (frame, mel), both channels in one pass over the band:
@@ -664,23 +670,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
         }
         if (pr + 1 < npairs) fetch(pr + 1);
         __syncthreads();
-        // X[j+1] = complex(realm0, realn1) = (entry.y, entry.x); entries >= n_freqs replicate the last
-        // kept one (grow); X[0] = 0; X[2048] keeps only its real part.  Z' = XA + i*XB, scaled by 1/N.
+        // X[j+1] = complex(realm0, realn1) = (entry.y, entry.x); entries >= n_freqs replicate the last kept one
+        // (grow); X[0] = 0; X[2048] keeps only its real part.  Lower slots (k < 2048) hold Z'[k] = XA + i*XB, upper
+        // slots Z'[k] = conj(XA[N-k]) + i*conj(XB[N-k]).  The 1/N of the inverse transform lives in the gain tables.
         float2 v[16];
-        constexpr float inv_n = 1.0f / 4096.0f;
+        {
+            const int top = nfq - 1;
+            const int elo = L.klow - 1;                 // entry of bin klow + 256 j          (lower slot j)
+            const int ehi = 255 - L.klow;               // entry of bin 4096 - (klow + 256 j)  (upper slot j: + 256 (15 - j))
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const int k = L.klow + 256 * j;
-            const int kk = (k <= 2048) ? k : 4096 - k;
-            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-            if (kk >= 1) {
-                int e = kk - 1; e = (e < nfq) ? e : nfq - 1;
-                const float2 ea = SA[e + (e >> 4)], eb = SB[e + (e >> 4)];
-                a = make_float2(ea.y, ea.x); b = make_float2(eb.y, eb.x);
-                if (kk == 2048) { a.y = 0.f; b.y = 0.f; }
-                if (k > 2048) { a.y = -a.y; b.y = -b.y; }
+            for (int j = 0; j < 8; j++) {
+                const int e = min(elo + 256 * j, top), q = e + (e >> 4);
+                const float2 ea = SA[max(q, 0)], eb = SB[max(q, 0)];
+                v[j] = join_lo(make_float2(ea.y, ea.x), make_float2(eb.y, eb.x));
             }
-            v[j] = make_float2((a.x - b.y) * inv_n, (a.y + b.x) * inv_n);
+#pragma unroll
+            for (int j = 8; j < 16; j++) {
+                const int e = min(ehi + 256 * (15 - j), top), q = e + (e >> 4);
+                const float2 ea = SA[q], eb = SB[q];
+                v[j] = join_hi(make_float2(ea.y, ea.x), make_float2(eb.y, eb.x));
+            }
+            if (L.special) {                            // klow == 0: bin 0 is zero, bin 2048 (slot 8) is real
+                v[0] = make_float2(0.f, 0.f);
+                const int e = min(2047, top), q = e + (e >> 4);
+                v[8] = make_float2(SA[q].y, SB[q].y);   // (Re XA, Re XB): Z'[2048] = Re XA + i Re XB
+            }
         }
         fft4096_inv(v, s, L);   // (the staging hand-over barrier above also orders the previous pair's pattern-(a) reads
                                 // before this pair's first exchange write)
