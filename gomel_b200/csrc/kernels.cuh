@@ -631,6 +631,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     float acc[NR];
 #pragma unroll
     for (int j = 0; j < KEEP; j++) acc[j] = 0.0f;
+    // interior pairs: a pair's 2*hop finished samples start at a multiple of 2*hop, so the periodic part of the
+    // window-sum gain a thread needs is the same ten values for every pair
+    float gm[SH];
+#pragma unroll
+    for (int j = 0; j < SH; j++) gm[j] = __ldg(p.gain_mid + (j * 256 + t) % H);
+    const long mid_lo = p.head_len, mid_hi = p.tl.sig_len - p.tail_len;
     // the first kPre*256 entries of a pair's two spectrogram rows are prefetched into registers one pair ahead
     constexpr int kPre = 6;                                   // covers NumFreqs <= 768
     float2 pre[kPre];
@@ -705,8 +711,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
             acc[m] = fmaf(v[m].x, w, acc[m]);
             acc[m + HS] = fmaf(v[m].y, w, acc[m + HS]);
         }
+        if (sbase + off0 >= mid_lo && sbase + off0 + SH * 256 <= mid_hi && (!has_prev || off0 >= HALO)) {
 #pragma unroll
-        for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
+            for (int j = 0; j < SH; j++) sout[off0 + j * 256 + t] = acc[j] * gm[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < SH; j++) st(off0 + j * 256, acc[j]);
+        }
 #pragma unroll
         for (int j = 0; j < KEEP; j++) acc[j] = acc[j + SH];
     }
