@@ -106,7 +106,11 @@ Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, 
         long tiles_wanted = (8 * slots + n_clips - 1) / n_clips;
         if (tiles_wanted < 1) tiles_wanted = 1;
         T = (int)((n_frames + tiles_wanted - 1) / tiles_wanted);
-        if (T < 16) T = 16;
+        // small batches are latency bound: allow tiles down to 4 frames until every CTA slot has a tile;
+        // large batches keep tiles >= 16 frames so the per-tile prologue stays amortised
+        const long tiles16 = (long)n_clips * ((n_frames + 15) / 16);
+        const int t_min = tiles16 >= slots ? 16 : (tiles16 * 2 >= slots ? 8 : 4);
+        if (T < t_min) T = t_min;
     }
     if (T & 1) T++;
     if (T < 4) T = 4;

@@ -189,3 +189,14 @@ def test_phase_quantise_blue_wrap_and_hdr(oracle):
     assert px16.dtype == np.uint16 and px16[:, :, 3].min() == 65535
     back, _, sr = oracle.phase_dequantise(px16, True, 0, True)
     assert np.abs(back - buf).max() < 0.02 * np.abs(buf).max() and sr == 48000.0
+
+
+def test_volume_boost_doubles_peak(oracle):
+    """test_phase_comprehensive.py:184-195: volume boost 2.0 doubles the peak of the reconstruction"""
+    wav = synth_clip(3, 0.6, sr=48000)
+    spec = oracle.to_phase(oracle.config(num_freqs=768), wav)
+    a = oracle.from_phase(oracle.config(num_freqs=768, volume_boost=1.0), spec)
+    b = oracle.from_phase(oracle.config(num_freqs=768, volume_boost=2.0), spec)
+    assert abs(np.abs(b).max() / np.abs(a).max() - 2.0) < 1e-12
+    c = oracle.from_phase(oracle.config(num_freqs=768, volume_boost=0.0), spec)     # 0 = no boost (phase/phase.go:146)
+    assert np.array_equal(a, c)
