@@ -558,7 +558,37 @@ def bench_to_mel(ctx, cfg, _lib, args):
         ctx.dev_free(p)
     ctx.host_free(own1)
     ctx.host_free(own2)
+    out["newmel_defaults"] = bench_newmel_defaults(ctx, _lib, base, n, timed)
+    ctx.set_mel_tables(cfg, 0.0, 16000.0)
     return out
+
+
+def bench_newmel_defaults(ctx, _lib, base, n, timed):
+    """mel.NewMel() defaults (mel/mel.go:30-41): 160 mels, fmax 8000, Window 256, Resolut 2048, GL 2 iterations.
+    Runs on the 4096-point core with zero-extended frames: 5x the frames per second of audio of the headline
+    geometry, each costing a full core transform."""
+    clips = 64
+    dcfg = _lib.make_config(n_fft=2048, hop=256, n_mels=160, n_freqs=0, gl_iters=2)
+    ctx.set_mel_tables(dcfg, 0.0, 8000.0)
+    npad, frames, ola = _lib.frames(dcfg, n)
+    stride = (npad + 3) & ~3
+    wav = np.zeros((clips, stride), np.float32)
+    for c in range(clips):
+        wav[c, :n] = base[c % len(base)]
+    d_sig = ctx.dev_malloc(wav.nbytes)
+    d_mel = ctx.dev_malloc(clips * frames * 160 * 2 * 4)
+    d_wav = ctx.dev_malloc(clips * ola * 4)
+    ctx.h2d(d_sig, wav)
+    res = {"workload": "%d x 10 s clips, %d frames each, device-resident" % (clips, frames)}
+    ms = timed(lambda: ctx.check(ctx.lib.gomel_to_mel_dev(ctx.h, C.byref(dcfg), d_sig, clips, stride, npad, frames, d_mel)))
+    res["to_mel"] = {"frames_per_s": clips * frames / (ms / 1e3), "audio_s_per_s": clips * CLIP_SECONDS / (ms / 1e3), "ms": ms}
+    ms = timed(lambda: ctx.check(ctx.lib.gomel_from_mel_dev(ctx.h, C.byref(dcfg), d_mel, clips, frames, None, 1, ola, d_wav)),
+               reps=10)
+    res["from_mel_gl2"] = {"frame_iterations_per_s": 2 * clips * frames / (ms / 1e3),
+                           "audio_s_per_s": clips * CLIP_SECONDS / (ms / 1e3), "ms": ms}
+    for p in (d_sig, d_mel, d_wav):
+        ctx.dev_free(p)
+    return res
 
 
 def main():

@@ -21,6 +21,16 @@ constexpr int kHS = 5;                       // hop slots: Window / 256 = 1280 /
 constexpr int kHop = 256 * kHS;
 constexpr int kHalo = (16 - kHS) * 256;      // Resolut - Window = 2816 samples shared by adjacent tiles
 
+// The frame geometry of one call.  Native: Resolut 4096 / Window 1280 (every cmd/* tool of the reference).
+// alt: Resolut 2048 / Window 256, the defaults of mel.NewMel (mel/mel.go:37-38), on the mel paths only; it
+// runs on the same 4096-point core with the frame zero-extended (even core bins = the 2048-point spectrum).
+struct Geo {
+    int n_fft = kN, hop = kHop, halo = kHalo;
+    bool alt = false;
+    long ola(long n_frames) const { return n_fft + (n_frames - 1) * (long)hop; }
+};
+constexpr int kAltHS = 1, kAltFS = 8;
+
 enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
                S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_COUNT };
 
@@ -33,9 +43,10 @@ struct gomel_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
     float4* d_tables = nullptr;
+    float4* d_tables_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     double* d_tables64 = nullptr;     // strict float64 path (built on first use)
     // mel tables
-    int tbl_mels = 0;
+    int tbl_mels = 0, tbl_bins = 0;
     int *d_fwd_lo = nullptr, *d_fwd_hi = nullptr, *d_inv_lo = nullptr, *d_inv_hi = nullptr;
     float* d_fwd_mod = nullptr;
     double* d_inv_mod = nullptr;
@@ -78,12 +89,16 @@ int ensure(gomel_ctx* ctx, int slot, size_t bytes, void** out)
     return 0;
 }
 
-int check_cfg(gomel_ctx* ctx, const gomel_config* cfg)
+int check_cfg(gomel_ctx* ctx, const gomel_config* cfg, Geo* geo = nullptr)
 {
     if (!cfg) return fail(ctx, GOMEL_E_ARG, "config is NULL");
-    if (cfg->n_fft != kN || cfg->hop != kHop)
-        return fail(ctx, GOMEL_E_UNSUPPORTED, "this build supports Resolut=4096, Window=1280 only");
-    return 0;
+    if (cfg->n_fft == kN && cfg->hop == kHop) { if (geo) *geo = Geo(); return 0; }
+    if (geo && cfg->n_fft == 256 * kAltFS && cfg->hop == 256 * kAltHS) {
+        geo->n_fft = cfg->n_fft; geo->hop = cfg->hop; geo->halo = cfg->n_fft - cfg->hop; geo->alt = true;
+        return 0;
+    }
+    return fail(ctx, GOMEL_E_UNSUPPORTED, geo ? "this build supports Resolut/Window = 4096/1280 and 2048/256 only"
+                                              : "this entry point supports Resolut=4096, Window=1280 only");
 }
 
 long pad_len(long n, int filter)            // mel/impl.go:429-455
@@ -95,7 +110,8 @@ long pad_len(long n, int filter)            // mel/impl.go:429-455
     return pad > 0 ? pad : 0;
 }
 
-Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len)
+// t_floor: a tile must be at least as long as the halo (samples are shared by at most two tiles)
+Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len, int t_floor = 4)
 {
     Tiling tl;
     tl.n_frames = (int)n_frames;
@@ -113,10 +129,10 @@ Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, 
         if (T < t_min) T = t_min;
     }
     if (T & 1) T++;
-    if (T < 4) T = 4;
+    if (T < t_floor) T = t_floor;
     const long fr_even = n_frames + (n_frames & 1);
     if (T > fr_even) T = (int)fr_even;
-    if (T < 4) T = 4;
+    if (T < t_floor) T = t_floor;
     tl.tile_frames = T;
     tl.n_tiles = (int)((n_frames + T - 1) / T);
     tl.edge_first = tl.edge_last = 0;
@@ -127,7 +143,7 @@ Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, 
 
 int grid_1d(long n, int block) { long g = (n + block - 1) / block; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 
-void build_fft_tables(std::vector<float>& blob)
+void build_fft_tables(std::vector<float>& blob, int n_win = kN)
 {
     blob.assign(kTableBytes / 4, 0.0f);
     float* T1 = blob.data();
@@ -147,10 +163,10 @@ void build_fft_tables(std::vector<float>& blob)
     fill(T1, kT1Mode, 256, 4096);
     fill(T2, kT2Mode, 16, 256);
     // symmetric Hann of gossp/go-dsp: 0.5*(1-cos(2 pi n/(N-1)))  (phase.py:122 np.hanning)
-    for (int m = 0; m < 8; m++)                      // first half only: w[n] = w[4095-n]
+    for (int m = 0; m < n_win / 512; m++)            // first half only: w[n] = w[N-1-n]
         for (int t = 0; t < 256; t++) {
             const int n = t + 256 * m;
-            win[m * 256 + t] = (float)(0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1))));
+            win[m * 256 + t] = (float)(0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(n_win - 1))));
         }
 }
 
@@ -212,16 +228,17 @@ int prepare_gain(gomel_ctx* ctx, long n_frames, double boost)
 int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_sig, int n_clips, long sig_stride,
             long sig_len, long n_frames, float* d_out)
 {
-    if (int rc = check_cfg(ctx, cfg)) return rc;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, mode == MODE_MEL ? &geo : nullptr)) return rc;
     if (!d_sig || !d_out || n_clips <= 0 || n_frames <= 0 || sig_stride < sig_len)
         return fail(ctx, GOMEL_E_ARG, "bad argument to forward transform");
-    if (sig_len < kN + (n_frames - 1) * (long)kHop)
+    if (sig_len < geo.ola(n_frames))
         return fail(ctx, GOMEL_E_ARG, "signal shorter than the frames requested");
     FwdParams p = {};
-    p.sig = d_sig; p.tables = ctx->d_tables;
+    p.sig = d_sig; p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
     p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, sig_len);
     if (mode == MODE_MEL) {
-        if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
+        if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels || cfg->n_fft / 2 != ctx->tbl_bins)
             return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
         p.fwd_lo = ctx->d_fwd_lo; p.fwd_hi = ctx->d_fwd_hi; p.fwd_mod = ctx->d_fwd_mod; p.n_mels = cfg->n_mels;
         p.mel_out = d_out;
@@ -234,7 +251,8 @@ int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_si
     const long grid = (long)n_clips * p.tl.n_tiles;
     if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
     CU(cudaEventRecord(ctx->ev_k0, ctx->st));
-    if (mode == MODE_MEL) k_stft_fwd<kHS, MODE_MEL><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
+    if (mode == MODE_MEL && geo.alt) k_stft_fwd<kAltHS, MODE_MEL, kAltFS><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
+    else if (mode == MODE_MEL) k_stft_fwd<kHS, MODE_MEL><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
     else if (mode == MODE_PHASE) k_stft_fwd<kHS, MODE_PHASE><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
     else k_stft_fwd<kHS, MODE_SPEC><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
     CU(cudaEventRecord(ctx->ev_k1, ctx->st));
@@ -247,7 +265,9 @@ int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_si
 int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_clips, long n_frames,
            const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
 {
-    const long ola = kN + (n_frames - 1) * (long)kHop;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
+    const long ola = geo.ola(n_frames);
     if (sig_stride < ola) return fail(ctx, GOMEL_E_ARG, "sig_stride < ola_len");
     if (d_init == d_out) return fail(ctx, GOMEL_E_ARG, "d_init and d_out must not alias");
     const int iters = cfg->gl_iters;
@@ -264,13 +284,13 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
         return 0;
     }
     SynParams p = {};
-    p.tables = ctx->d_tables;
-    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola);
+    p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
+    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4);
     p.mags = d_mags;
     void *tmp = nullptr, *hb[2] = { nullptr, nullptr };
     if (iters > 1) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &tmp)) return rc; }
     p.hb_tiles = p.tl.n_tiles + 1; p.tile_lo = 0; p.tiles_in_launch = p.tl.n_tiles;
-    const size_t hb_bytes = (size_t)n_clips * p.hb_tiles * kHalo * 4 + 16;
+    const size_t hb_bytes = (size_t)n_clips * p.hb_tiles * geo.halo * 4 + 16;
     if (int rc = ensure(ctx, S_HB0, hb_bytes, &hb[0])) return rc;
     if (int rc = ensure(ctx, S_HB1, hb_bytes, &hb[1])) return rc;
     const long grid = (long)n_clips * p.tl.n_tiles;
@@ -282,15 +302,16 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
         p.sig_in = cur; p.sig_out = dst;
         p.hb_in = (i == 0) ? nullptr : (const float*)hb[(i - 1) & 1];
         p.hb_out = (float*)hb[i & 1];
-        k_gl_iter<kHS><<<(unsigned)grid, kThreads, kGlSmemBytes, ctx->st>>>(p);
+        if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<(unsigned)grid, kThreads, kGlSmemBytes, ctx->st>>>(p);
+        else k_gl_iter<kHS><<<(unsigned)grid, kThreads, kGlSmemBytes, ctx->st>>>(p);
         ctx->launches++;
         cur = dst;
     }
     CU(cudaEventRecord(ctx->ev_k1, ctx->st));
     ctx->hot_launches = iters;
     if (p.tl.n_tiles > 1) {
-        const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;
-        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, kHop, kHalo,
+        const long total = (long)(p.tl.n_tiles - 1) * geo.halo * n_clips;
+        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, geo.hop, geo.halo,
                                                            n_clips, 0, 1, p.hb_tiles, p);
         ctx->launches++;
     }
@@ -301,13 +322,18 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
 template <typename T>
 int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, float* d_mags)
 {
-    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
+    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels || cfg->n_fft / 2 != ctx->tbl_bins)
         return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
     if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
     long g = (n_rows + kMagsRowsPerPass - 1) / kMagsRowsPerPass;
     if (g > 148L * 8) g = 148L * 8;
-    k_mags_from_mel<T><<<(unsigned)g, 256, (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double), ctx->st>>>(
-        d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+    const size_t sm = (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double);
+    if (cfg->n_fft == 256 * kAltFS)
+        k_mags_from_mel<T, kAltFS><<<(unsigned)g, 256, sm, ctx->st>>>(
+            d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+    else
+        k_mags_from_mel<T><<<(unsigned)g, 256, sm, ctx->st>>>(
+            d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     ctx->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -317,7 +343,8 @@ template <typename T>
 int from_mel_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, int n_clips, long n_frames,
                       const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
 {
-    if (int rc = check_cfg(ctx, cfg)) return rc;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     if (!d_mel || !d_out || n_clips <= 0 || n_frames <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument to from_mel");
     void* mags;
     if (int rc = ensure(ctx, S_MAGS, (size_t)n_clips * n_frames * kMagStride * 4, &mags)) return rc;
@@ -364,7 +391,7 @@ int from_mel_f64(gomel_ctx* ctx, const gomel_config* cfg, const double* d_mel, l
                  unsigned long long seed, double* h_out)
 {
     using namespace gomel::f64;
-    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels)
+    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels || cfg->n_fft / 2 != ctx->tbl_bins)
         return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
     if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
     const long ola = kN + (n_frames - 1) * (long)kHop;
@@ -435,7 +462,7 @@ struct Guard {
 // =================================================================== exported C ABI
 extern "C" {
 
-const char* gomel_version(void) { return "gomel_b200 0.1 (sm_100a, Resolut 4096 / Window 1280)"; }
+const char* gomel_version(void) { return "gomel_b200 0.1 (sm_100a, Resolut/Window 4096/1280; mel paths also 2048/256)"; }
 
 int gomel_ctx_create(int device, gomel_ctx** out)
 {
@@ -461,6 +488,11 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         build_fft_tables(blob);
         CU(cudaMalloc(&ctx->d_tables, kTableBytes));
         CU(cudaMemcpy(ctx->d_tables, blob.data(), kTableBytes, cudaMemcpyHostToDevice));
+        build_fft_tables(blob, 256 * kAltFS);
+        CU(cudaMalloc(&ctx->d_tables_alt, kTableBytes));
+        CU(cudaMemcpy(ctx->d_tables_alt, blob.data(), kTableBytes, cudaMemcpyHostToDevice));
+        if (int rc = set_smem_attr(ctx, k_stft_fwd<kAltHS, MODE_MEL, kAltFS>)) return rc;
+        CU(cudaFuncSetAttribute(k_gl_iter<kAltHS, kAltFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_MEL>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_PHASE>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_SPEC>)) return rc;
@@ -481,6 +513,7 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaStreamSynchronize(ctx->st);
     for (int i = 0; i < S_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_tables_alt);
     cudaFree(ctx->d_tables64);
     cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
     cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
@@ -523,8 +556,9 @@ int gomel_set_mel_tables(gomel_ctx* ctx, const gomel_config* cfg, const int* fwd
 {
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
-    if (int rc = check_cfg(ctx, cfg)) return rc;
-    const int mels = cfg->n_mels, B = kN / 2;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
+    const int mels = cfg->n_mels, B = geo.n_fft / 2;
     if (mels <= 0 || mels > 4096 || !fwd_lo || !fwd_hi || !fwd_mod || !inv_lo || !inv_hi || !inv_mod)
         return fail(ctx, GOMEL_E_ARG, "bad mel table arguments");
     // index ranges the reference would panic on (mel/impl.go:331-338, :366-377) are refused here
@@ -542,7 +576,7 @@ int gomel_set_mel_tables(gomel_ctx* ctx, const gomel_config* cfg, const int* fwd
     cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
     cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
     ctx->d_fwd_lo = ctx->d_fwd_hi = ctx->d_inv_lo = ctx->d_inv_hi = nullptr; ctx->d_fwd_mod = nullptr; ctx->d_inv_mod = nullptr;
-    ctx->tbl_mels = 0;
+    ctx->tbl_mels = ctx->tbl_bins = 0;
     std::vector<float> fm(mels);
     for (int i = 0; i < mels; i++) fm[i] = (float)fwd_mod[i];
     CU(cudaMalloc(&ctx->d_fwd_lo, mels * 4)); CU(cudaMalloc(&ctx->d_fwd_hi, mels * 4)); CU(cudaMalloc(&ctx->d_fwd_mod, mels * 4));
@@ -553,14 +587,15 @@ int gomel_set_mel_tables(gomel_ctx* ctx, const gomel_config* cfg, const int* fwd
     CU(cudaMemcpy(ctx->d_inv_lo, inv_lo, B * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_inv_hi, inv_hi, B * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_inv_mod, inv_mod, B * 8, cudaMemcpyHostToDevice));
-    ctx->tbl_mels = mels;
+    ctx->tbl_mels = mels; ctx->tbl_bins = B;
     return 0;
 }
 
 // ------------------------------------------------------------------- host-buffer API
 static int host_forward(gomel_ctx* ctx, const gomel_config* cfg, int mode, const double* wav, long n, double* out)
 {
-    if (int rc = check_cfg(ctx, cfg)) return rc;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, mode == MODE_MEL ? &geo : nullptr)) return rc;
     if (!wav || !out || n <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
     long np, fr, ola;
     if (gomel_frames(cfg, n, &np, &fr, &ola)) return fail(ctx, GOMEL_E_ARG, "bad length");
@@ -601,9 +636,10 @@ int gomel_from_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* mel, l
 {
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
-    if (int rc = check_cfg(ctx, cfg)) return rc;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, (cfg && (cfg->flags & GOMEL_FLAG_F64)) ? nullptr : &geo)) return rc;
     if (!mel || !wav_out || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
-    const long ola = kN + (n_frames - 1) * (long)kHop;
+    const long ola = geo.ola(n_frames);
     const long n_mel = n_frames * 2L * cfg->n_mels;
     void *dmel, *dinit64 = nullptr, *dinit = nullptr, *dout, *dout64;
     if (int rc = ensure(ctx, S_F64IN, (size_t)n_mel * 8, &dmel)) return rc;
@@ -859,9 +895,10 @@ int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const flo
 {
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
-    if (int rc = check_cfg(ctx, cfg)) return rc;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     if (!mel || !out || n_clips <= 0 || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
-    const long ola = kN + (n_frames - 1) * (long)kHop;
+    const long ola = geo.ola(n_frames);
     const long mel_per = n_frames * 2L * cfg->n_mels;
     int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
     if (cpc > n_clips) cpc = n_clips;
@@ -925,7 +962,8 @@ int gomel_to_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float
 {
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
-    if (int rc = check_cfg(ctx, cfg)) return rc;
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     if (!wav || !mel_out || n_clips <= 0 || n_samples <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
     long np, fr, ola;
     if (gomel_frames(cfg, n_samples, &np, &fr, &ola)) return fail(ctx, GOMEL_E_ARG, "bad length");

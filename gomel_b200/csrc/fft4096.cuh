@@ -66,11 +66,13 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base)
     return s;
 }
 
-// Hann coefficient of sample n = t + 256*m.  The window is symmetric (w[n] = w[4095-n]), only its first half is
-// kept in shared memory; both access patterns are unit-stride across a warp.
+// Hann coefficient of sample n = t + 256*m of an FS*256-sample frame.  The window is symmetric
+// (w[n] = w[N-1-n]), only its first half is kept in shared memory; both access patterns are unit-stride
+// across a warp.
+template <int FS = 16>
 __device__ __forceinline__ float win_at(const float* win, int m, int t)
 {
-    return (m < 8) ? win[m * 256 + t] : win[(15 - m) * 256 + (255 - t)];
+    return (m < FS / 2) ? win[m * 256 + t] : win[(FS - 1 - m) * 256 + (255 - t)];
 }
 
 // global table blob layout == smem table layout (T1 | T2 | win), kTableBytes long

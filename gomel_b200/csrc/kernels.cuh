@@ -149,14 +149,17 @@ struct FwdParams {
     float2* spec_out;
 };
 
-template <int HS, int MODE>
+// FS = frame slots (Resolut / 256).  FS = 16 is the native frame.  FS = 8 (Resolut 2048, the mel.NewMel default)
+// runs the same 4096-point core on the frame zero-extended to 4096 samples: X2048[k] = X4096[2k].
+template <int HS, int MODE, int FS = 16>
 __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
     const Lanes L = make_lanes();
     load_tables(s, p.tables, L.t);
-    constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS;
+    static_assert(FS == 16 || (FS == 8 && MODE == MODE_MEL), "only the mel forward path has the Resolut 2048 variant");
+    constexpr int NR = FS + HS, SH = 2 * HS, KEEP = FS - HS, H = 256 * HS;
     const int tile = blockIdx.x % p.tl.n_tiles, clip = blockIdx.x / p.tl.n_tiles;
     const int f0 = tile_begin(p.tl, tile);
     const int nf = tile_begin(p.tl, tile + 1) - f0;
@@ -188,7 +191,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
         }
         float2 v[16];
 #pragma unroll
-        for (int m = 0; m < 16; m++) { const float w = win_at(s.win, m, t); v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
+        for (int m = 0; m < 16; m++) {
+            if (m < FS) { const float w = win_at<FS>(s.win, m, t); v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
+            else v[m] = make_float2(0.f, 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < KEEP; j++) raw[j] = raw[j + SH];
 
@@ -220,15 +226,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
         if (MODE == MODE_MEL) {
             float* SA = reinterpret_cast<float*>(stg);
             float* SB = SA + 2184;
+            // staged by bin of the configured transform: FS = 8 keeps the even bins of the 4096-point core
+            if (FS == 16 || (L.klow & 1) == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = L.klow + 256 * j, q = k + (k >> 4);
-                SA[q] = sqrt_fast(fmaf(xa[j].x, xa[j].x, xa[j].y * xa[j].y));
-                SB[q] = sqrt_fast(fmaf(xb[j].x, xb[j].x, xb[j].y * xb[j].y));
+                for (int j = 0; j < 8; j++) {
+                    const int k = (L.klow + 256 * j) >> (FS == 16 ? 0 : 1), q = k + (k >> 4);
+                    SA[q] = sqrt_fast(fmaf(xa[j].x, xa[j].x, xa[j].y * xa[j].y));
+                    SB[q] = sqrt_fast(fmaf(xb[j].x, xb[j].x, xb[j].y * xb[j].y));
+                }
             }
             if (L.special) {
-                SA[2048 + 128] = sqrt_fast(fmaf(xa[8].x, xa[8].x, xa[8].y * xa[8].y));
-                SB[2048 + 128] = sqrt_fast(fmaf(xb[8].x, xb[8].x, xb[8].y * xb[8].y));
+                constexpr int qn = FS * 128 + FS * 8;        // Nyquist bin FS*128, padded
+                SA[qn] = sqrt_fast(fmaf(xa[8].x, xa[8].x, xa[8].y * xa[8].y));
+                SB[qn] = sqrt_fast(fmaf(xb[8].x, xb[8].x, xb[8].y * xb[8].y));
             }
             __syncthreads();
             // domel (mel/impl.go:310-345): one work item = (frame, mel), both channels in one pass over the band:
@@ -319,7 +329,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
 // (the IFFT normalisation) and stored in mag_pos() order.  Arithmetic in float64.
 constexpr int kMagsRowsPerPass = 4;       // frames handled together by one CTA pass (amortises the barriers)
 
-template <typename T>
+// FS = 8 (Resolut 2048): bin k' of the 2048-point transform sits where bin 2k' of the 4096-point core is read,
+// the odd core bins are zero, and the scale is 1/2048 (the core's unnormalised inverse of the even-bin spectrum
+// is 2048 times the reference's IFFT).
+template <typename T, int FS = 16>
 __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel, float* __restrict__ mags,
                                                        const int* __restrict__ inv_lo, const int* __restrict__ inv_hi,
                                                        const double* __restrict__ inv_mod, int n_mels,
@@ -334,14 +347,19 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
         for (int i = threadIdx.x; i < nr * per_row; i += blockDim.x) e[i] = exp((double)m[i]);
         __syncthreads();
         for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes in mag_pos order
-            const int i = mag_unpos(pos);
+            const int kc = mag_unpos(pos);
+            if (FS == 8 && (kc & 1)) {
+                for (int r = 0; r < nr; r++) mags[(row0 + r) * kMagStride + pos] = 0.0f;
+                continue;
+            }
+            const int i = kc >> (FS == 16 ? 0 : 1);
             const int lo = inv_lo[i], hi = inv_hi[i];
             const bool copy = lo == hi, lerp = (lo + 1 == hi) && hi < n_mels;
             const double md = lerp ? inv_mod[i] : 0.0;
             for (int r = 0; r < nr; r++) {
                 const double* er = e + r * per_row;
                 float* out = mags + (row0 + r) * kMagStride;
-                const int nch = (i == 2047) ? 2 : 1;
+                const int nch = (i == FS * 128 - 1) ? 2 : 1;
                 for (int l = 0; l < nch; l++) {
                     double total = 0.0;
                     if (copy) total = er[2 * lo + l];
@@ -352,7 +370,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                         for (int k = lo; k < hi; k++) total += er[2 * k + l];
                         total /= (double)(hi - lo + 1);
                     }
-                    const double v = fabs((total - tune_add) / tune_mul) * (1.0 / 4096.0);
+                    const double v = fabs((total - tune_add) / tune_mul) * (1.0 / (256.0 * FS));
                     out[l ? 2048 : pos] = (float)v;
                 }
             }
@@ -410,7 +428,7 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 constexpr int kGlMagBytes = 2 * kMagStride * 4;                 // two magnitude rows (frames A and B)
 constexpr int kGlSmemBytes = kSmemBytes + kGlMagBytes + 16 + 256;   // + one mbarrier + the special coset's scratch
 
-template <int HS>
+template <int HS, int FS = 16>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -420,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     float2* const zsc = reinterpret_cast<float2*>(smem_raw + kSmemBytes + kGlMagBytes + 16);   // [2][16]
     const Lanes L = make_lanes();
     load_tables(s, p.tables, L.t);
-    constexpr int NR = 16 + HS, SH = 2 * HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
+    constexpr int NR = FS + HS, SH = 2 * HS, KEEP = FS - HS, H = 256 * HS, HALO = KEEP * 256;
     int tile, clip;
     if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
     else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = blockIdx.x / p.tiles_in_launch; }
@@ -462,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     };
 
     if (t == 0) mbar_init(bar, 1);
-    float raw[NR], acc[NR], nxt[SH], win[16];
+    float raw[NR], acc[NR], nxt[SH], win[FS];
 #pragma unroll
     for (int j = 0; j < KEEP; j++) { raw[j] = ld(j * 256); acc[j] = 0.0f; }
 #pragma unroll
@@ -472,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
     __syncthreads();                // tables + mbarrier init visible
 #pragma unroll
-    for (int m = 0; m < 16; m++) win[m] = win_at(s.win, m, t);
+    for (int m = 0; m < FS; m++) win[m] = win_at<FS>(s.win, m, t);
 
     for (int pr = 0; pr < npairs; pr++) {
         const int off0 = pr * 2 * H;
@@ -488,7 +506,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         for (int j = 0; j < SH; j++) { raw[KEEP + j] = nxt[j]; acc[KEEP + j] = 0.0f; }
         float2 v[16];
 #pragma unroll
-        for (int m = 0; m < 16; m++) v[m] = make_float2(raw[m] * win[m], raw[m + HS] * win[m]);
+        for (int m = 0; m < 16; m++) {
+            if (m < FS) v[m] = make_float2(raw[m] * win[m], raw[m + HS] * win[m]);
+            else v[m] = make_float2(0.f, 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < KEEP; j++) raw[j] = raw[j + SH];
 
@@ -566,8 +587,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
         // the Hann coefficients are read once per pair: here for the synthesis window, then kept in
         // registers for the next pair's analysis window (not live across the transforms)
 #pragma unroll
-        for (int m = 0; m < 16; m++) {
-            win[m] = win_at(s.win, m, t);
+        for (int m = 0; m < FS; m++) {
+            win[m] = win_at<FS>(s.win, m, t);
             acc[m] = fmaf(v[m].x, win[m], acc[m]);
             acc[m + HS] = fmaf(v[m].y, win[m], acc[m + HS]);
         }

@@ -13,8 +13,10 @@
  *   - a context owns one device, one stream and grow-only scratch; calls on one context are
  *     serialised by an internal mutex and may come from any OS thread (cgo hops threads).
  *   - this build supports Resolut (n_fft) = 4096 and Window (hop) = 1280 (the configuration of
- *     cmd/tomel, cmd/towav, cmd/tophase, cmd/fromphase and of NewPhase); anything else returns
- *     GOMEL_E_UNSUPPORTED.  There is NO CPU fallback.
+ *     cmd/tomel, cmd/towav, cmd/tophase, cmd/fromphase and of NewPhase) on every entry point,
+ *     and Resolut 2048 / Window 256 (the mel.NewMel defaults, mel/mel.go:37-38) on the float32
+ *     mel entry points (gomel_to_mel*, gomel_from_mel* without GOMEL_FLAG_F64,
+ *     gomel_set_mel_tables); anything else returns GOMEL_E_UNSUPPORTED.  There is NO CPU fallback.
  */
 #ifndef GOMEL_CUDA_H
 #define GOMEL_CUDA_H
@@ -31,7 +33,7 @@ typedef enum {
     GOMEL_E_ARG = -1,          /* bad argument, incl. len % n_mels != 0 where Go panics (mel/impl.go:366-372) */
     GOMEL_E_CUDA = -2,         /* CUDA runtime error */
     GOMEL_E_NOMEM = -3,        /* device or pinned allocation failed */
-    GOMEL_E_UNSUPPORTED = -4,  /* configuration outside this build (n_fft != 4096, hop != 1280) */
+    GOMEL_E_UNSUPPORTED = -4,  /* Resolut / Window outside this build (see above) */
     GOMEL_E_STATE = -5         /* call order, e.g. mel tables not set */
 } gomel_status;
 

@@ -33,7 +33,23 @@ int main()
     // ---- mel: the cmd/tomel configuration
     mel::Mel* m = mel::NewMel();
     if (m->NumMels != 160 || m->Window != 256 || m->Resolut != 2048) { printf("NewMel defaults wrong\n"); bad++; }
-    {   // NewMel defaults are outside this build: must fail loudly, not fall back
+    {   // NewMel defaults (Window 256 / Resolut 2048) run as they are
+        orc_config od{};
+        od.num_mels = 160; od.num_freqs = 768; od.window = 256; od.resolut = 2048; od.mel_fmin = 0; od.mel_fmax = 8000;
+        od.tune_mul = 1; od.tune_add = 0; od.volume_boost = 0; od.gl_iters = 2;
+        auto r = m->ToMel(wav);
+        if (!r.second.empty()) { printf("ToMel (defaults) error: %s\n", r.second.c_str()); return 1; }
+        const long fr = (long)r.first.size() / 160;
+        std::vector<double> om(r.first.size() * 2);
+        if (orc_to_mel(&od, wav.data(), n, om.data(), (long)om.size()) != fr) { printf("oracle frames differ (defaults)\n"); bad++; }
+        std::vector<double> a(om.size()), b(om.size());
+        for (size_t i = 0; i < om.size(); i++) { a[i] = std::exp((&r.first[0][0])[i]); b[i] = std::exp(om[i]); }
+        const double e = rel_l2(a.data(), b.data(), a.size());
+        printf("ToMel    (NewMel defaults) frames=%ld rel-L2(linear)=%.3e\n", fr, e);
+        if (!(e < 1e-5)) bad++;
+    }
+    {   // a geometry outside this build must fail loudly, not fall back
+        m->Window = 512; m->Resolut = 1024;
         auto r = m->ToMel(wav);
         if (r.second.empty()) { printf("unsupported config did not fail\n"); bad++; }
     }

@@ -154,7 +154,8 @@ def test_from_mel_bad_length_is_an_error(mctx, lib):
 
 def test_unsupported_config_fails_loudly(mctx, lib):
     from gomel_b200 import NewMel
-    m = NewMel()                                                # NewMel defaults: Window 256, Resolut 2048
+    m = NewMel()
+    m.Window, m.Resolut = 512, 1024                             # neither 1280/4096 nor NewMel's 256/2048
     with pytest.raises(lib.GomelError) as e:
         m.ToMel(np.zeros(10000))
     assert e.value.code == lib.E_UNSUPPORTED
