@@ -303,7 +303,7 @@ def run_product(args):
                     traffic = tj["dram_bytes_per_frame_iter"] * clips * frames
                 except Exception:
                     traffic = None
-            roofline = {"bound": "hbm", "kernel": "k_gl_iter<5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            roofline = {"bound": "hbm", "kernel": "k_gl_iter<5, 16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": BYTES_PER_FRAME_ITER * clips * frames,
                         "avg_launch_ms": per_launch_s * 1e3, "launches_timed": hot_n,
