@@ -23,19 +23,22 @@ import (
 type Config struct {
 	NFFT, Hop, NMels, NFreqs, GLIters int
 	TuneMul, TuneAdd, VolumeBoost     float64
+	MelFmin, MelFmax                  float64 // key of the filterbank tables (with NFFT, NMels)
 }
 
 func (c Config) c() C.gomel_config {
 	return C.gomel_config{n_fft: C.int(c.NFFT), hop: C.int(c.Hop), n_mels: C.int(c.NMels), n_freqs: C.int(c.NFreqs),
 		gl_iters: C.int(c.GLIters), tune_mul: C.double(c.TuneMul), tune_add: C.double(c.TuneAdd),
-		volume_boost: C.double(c.VolumeBoost)}
+		volume_boost: C.double(c.VolumeBoost), mel_fmin: C.double(c.MelFmin), mel_fmax: C.double(c.MelFmax)}
 }
 
-// Ctx owns one gomel_ctx.  Methods are safe for concurrent use (the library serialises per context);
-// use one Ctx per goroutine pool slot for concurrency.
+// Ctx owns one gomel_ctx.  Methods are safe for concurrent use: the library serialises calls per context
+// and keeps the mel filterbank tables by key (NFFT, NMels, MelFmin, MelFmax), so goroutines with different
+// Mel configurations can share one Ctx.  Use several Ctx for GPU-side concurrency.
 type Ctx struct {
-	h         *C.gomel_ctx
-	tablesKey [4]float64
+	h          *C.gomel_ctx
+	mu         sync.Mutex
+	registered map[[4]float64]bool
 }
 
 var (
@@ -56,7 +59,7 @@ func New(device int) (*Ctx, error) {
 	if rc := C.gomel_ctx_create(C.int(device), &h); rc != 0 {
 		return nil, fmt.Errorf("gomel_ctx_create: %d (no CUDA device?)", int(rc))
 	}
-	return &Ctx{h: h}, nil
+	return &Ctx{h: h, registered: map[[4]float64]bool{}}, nil
 }
 
 func (x *Ctx) Close() { C.gomel_ctx_destroy(x.h); x.h = nil }
@@ -84,11 +87,15 @@ func melToHz(v float64) float64 { return 700.0 * (math.Exp(v/1127.0) - 1.0) } //
 // SetMelTables computes the (int(inlo), int(inhi), modlo) triples of domel / undomel with Go's own
 // math.Exp / math.Log -- exactly the expressions of mel/impl.go:313-323 and :350-360 -- and hands
 // them to the library, so the two 1-ulp-fragile band edges fall where the reference puts them.
+// Registered once per key; cfg.MelFmin / cfg.MelFmax of the compute calls select the set.
 func (x *Ctx) SetMelTables(cfg Config, fmin, fmax float64) error {
 	key := [4]float64{float64(cfg.NFFT), float64(cfg.NMels), fmin, fmax}
-	if x.tablesKey == key {
+	x.mu.Lock()
+	defer x.mu.Unlock()
+	if x.registered[key] {
 		return nil
 	}
+	cfg.MelFmin, cfg.MelFmax = fmin, fmax
 	fs, mels := cfg.NFFT/2, cfg.NMels
 	flo, fhi, fmod := make([]C.int, mels), make([]C.int, mels), make([]C.double, mels)
 	melbin := hzToMel(fmax) / float64(mels)
@@ -118,7 +125,10 @@ func (x *Ctx) SetMelTables(cfg Config, fmin, fmax float64) error {
 	if e := x.err(C.gomel_set_mel_tables(x.h, &cc, &flo[0], &fhi[0], &fmod[0], &ilo[0], &ihi[0], &imod[0])); e != nil {
 		return e
 	}
-	x.tablesKey = key
+	if len(x.registered) >= 48 { // the library keeps 64 sets (LRU); stay below that
+		x.registered = map[[4]float64]bool{}
+	}
+	x.registered[key] = true
 	return nil
 }
 

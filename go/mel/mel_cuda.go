@@ -13,7 +13,7 @@ import (
 
 func (m *Mel) cudaConfig() gomelcuda.Config {
 	return gomelcuda.Config{NFFT: m.Resolut, Hop: m.Window, NMels: m.NumMels, GLIters: m.GriffinLimIterations,
-		TuneMul: m.TuneMul, TuneAdd: m.TuneAdd, VolumeBoost: m.VolumeBoost}
+		TuneMul: m.TuneMul, TuneAdd: m.TuneAdd, VolumeBoost: m.VolumeBoost, MelFmin: m.MelFmin, MelFmax: m.MelFmax}
 }
 
 // ToMel replaces mel/mel.go:46-74.

@@ -24,7 +24,7 @@ class Config(C.Structure):
     """gomel_config (include/gomel_cuda.h)"""
     _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("n_mels", C.c_int), ("n_freqs", C.c_int),
                 ("gl_iters", C.c_int), ("tune_mul", C.c_double), ("tune_add", C.c_double),
-                ("volume_boost", C.c_double), ("flags", C.c_int)]
+                ("volume_boost", C.c_double), ("flags", C.c_int), ("mel_fmin", C.c_double), ("mel_fmax", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -89,7 +89,7 @@ SIGNATURES = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()         # re-entrant: default_context() creates a Context (-> load()) under it
 
 
 def load():
@@ -113,8 +113,10 @@ FLAG_F64 = 1          # strict float64 Griffin-Lim (include/gomel_cuda.h GOMEL_F
 
 
 def make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=2, tune_mul=1.0, tune_add=0.0,
-                volume_boost=0.0, flags=0):
-    return Config(n_fft, hop, n_mels, n_freqs, gl_iters, tune_mul, tune_add, volume_boost, flags)
+                volume_boost=0.0, flags=0, mel_fmin=0.0, mel_fmax=0.0):
+    """mel_fmin / mel_fmax select the registered filterbank tables (Context.set_mel_tables); both 0 = the most
+    recently registered tables for (n_fft, n_mels)."""
+    return Config(n_fft, hop, n_mels, n_freqs, gl_iters, tune_mul, tune_add, volume_boost, flags, mel_fmin, mel_fmax)
 
 
 def frames(cfg, n_samples):
@@ -174,7 +176,9 @@ class Context:
             raise GomelError(rc, "gomel_ctx_create failed (no CUDA device? gomel_b200 has no CPU fallback)")
         self.h = h
         self.device = device
-        self._tables_key = None
+        self._tables_key = None          # last set registered by set_mel_tables (the "most recent" one)
+        self._registered = set()         # keys registered so far (bounded; the library keeps 64 sets, LRU)
+        self._lock = threading.RLock()
 
     def close(self):
         if getattr(self, "h", None):
@@ -191,15 +195,47 @@ class Context:
         if rc:
             raise GomelError(rc, self.lib.gomel_last_error(self.h).decode())
 
-    def set_mel_tables(self, cfg, fmin, fmax):
-        key = (cfg.n_fft, cfg.n_mels, float(fmin), float(fmax))
-        if self._tables_key == key:
-            return
-        flo, fhi, fmod, ilo, ihi, imod = mel_tables(cfg.n_fft // 2, cfg.n_mels, float(fmin), float(fmax))
+    def _register(self, key):
+        n_fft, n_mels, fmin, fmax = key
+        kcfg = make_config(n_fft=n_fft, hop=256 if n_fft == 2048 else 1280, n_mels=n_mels, mel_fmin=fmin, mel_fmax=fmax)
+        flo, fhi, fmod, ilo, ihi, imod = mel_tables(n_fft // 2, n_mels, fmin, fmax)
         self.check(self.lib.gomel_set_mel_tables(
-            self.h, C.byref(cfg), flo.ctypes.data_as(_ip), fhi.ctypes.data_as(_ip), fmod.ctypes.data_as(_dp),
+            self.h, C.byref(kcfg), flo.ctypes.data_as(_ip), fhi.ctypes.data_as(_ip), fmod.ctypes.data_as(_dp),
             ilo.ctypes.data_as(_ip), ihi.ctypes.data_as(_ip), imod.ctypes.data_as(_dp)))
-        self._tables_key = key
+        if len(self._registered) >= 48:
+            self._registered.clear()
+        self._registered.add(key)
+
+    def set_mel_tables(self, cfg, fmin, fmax):
+        """Registers the filterbank tables of (cfg.n_fft, cfg.n_mels, fmin, fmax) and makes them the context's most
+        recent set -- the one every config with mel_fmin = mel_fmax = 0 uses.  For one configuration at a time;
+        callers that share a context across threads with different configurations use use_mel_tables()."""
+        key = (cfg.n_fft, cfg.n_mels, float(fmin), float(fmax))
+        with self._lock:
+            if self._tables_key == key:
+                return
+            self._register(key)
+            self._tables_key = key
+
+    def use_mel_tables(self, cfg, fmin, fmax):
+        """Stamps the table key (MelFmin, MelFmax) into `cfg` and registers that set once.  The mel entry points
+        look the set up by the key of the cfg they are given, so threads with different Mel configurations can
+        share this context: there is no context-wide "current tables" state on this path."""
+        key = (cfg.n_fft, cfg.n_mels, float(fmin), float(fmax))
+        cfg.mel_fmin, cfg.mel_fmax = key[2], key[3]
+        with self._lock:
+            self._tables_key = None          # a keyed use may reorder the library's most-recent list
+            if key not in self._registered:
+                self._register(key)
+
+    def _mel_call(self, cfg, call):
+        """Runs a mel entry point; if the library has evicted the cfg's table set meanwhile, registers it again."""
+        rc = call()
+        if rc == E_STATE and (cfg.mel_fmin != 0 or cfg.mel_fmax != 0):
+            with self._lock:
+                self._register((cfg.n_fft, cfg.n_mels, cfg.mel_fmin, cfg.mel_fmax))
+            rc = call()
+        self.check(rc)
 
     def launch_count(self):
         return int(self.lib.gomel_launch_count(self.h))
@@ -212,8 +248,8 @@ class Context:
         wav = np.ascontiguousarray(wav, np.float64)
         _, fr, _ = frames(cfg, len(wav))
         out = np.empty((fr * cfg.n_mels, 2), np.float64)
-        self.check(self.lib.gomel_to_mel(self.h, C.byref(cfg), wav.ctypes.data_as(_dp), len(wav),
-                                         out.ctypes.data_as(_dp)))
+        self._mel_call(cfg, lambda: self.lib.gomel_to_mel(self.h, C.byref(cfg), wav.ctypes.data_as(_dp), len(wav),
+                                                          out.ctypes.data_as(_dp)))
         return out
 
     def from_mel(self, cfg, mel, init=None, seed=0):
@@ -230,8 +266,8 @@ class Context:
                 raise GomelError(E_ARG, "init signal length != ola_len")
             ip = init.ctypes.data_as(_dp)
         out = np.empty(ola, np.float64)
-        self.check(self.lib.gomel_from_mel(self.h, C.byref(cfg), mel.ctypes.data_as(_dp), fr, ip, seed,
-                                           out.ctypes.data_as(_dp)))
+        self._mel_call(cfg, lambda: self.lib.gomel_from_mel(self.h, C.byref(cfg), mel.ctypes.data_as(_dp), fr, ip, seed,
+                                                            out.ctypes.data_as(_dp)))
         return out
 
     def to_phase(self, cfg, wav):
@@ -339,8 +375,6 @@ def default_context(device=0):
     """Process-wide context per device (what the drop-in classes use)."""
     with _lock:
         ctx = _default.get(device)
-    if ctx is None:
-        ctx = Context(device)
-        with _lock:
-            _default[device] = ctx
+        if ctx is None:
+            ctx = _default[device] = Context(device)
     return ctx

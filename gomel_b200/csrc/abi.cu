@@ -31,6 +31,23 @@ struct Geo {
 };
 constexpr int kAltHS = 1, kAltFS = 8;
 
+// One registered set of domel / undomel tables.  Keyed by (Resolut, NumMels, MelFmin, MelFmax) so that callers
+// with different Mel configurations can share a context concurrently (set + compute are two calls).
+struct MelTables {
+    int n_fft = 0, n_mels = 0;
+    double fmin = 0, fmax = 0;
+    int *fwd_lo = nullptr, *fwd_hi = nullptr, *inv_lo = nullptr, *inv_hi = nullptr;
+    float* fwd_mod = nullptr;
+    double* inv_mod = nullptr;
+    void release()
+    {
+        cudaFree(fwd_lo); cudaFree(fwd_hi); cudaFree(fwd_mod); cudaFree(inv_lo); cudaFree(inv_hi); cudaFree(inv_mod);
+        fwd_lo = fwd_hi = inv_lo = inv_hi = nullptr; fwd_mod = nullptr; inv_mod = nullptr;
+    }
+};
+constexpr size_t kMaxMelTables = 64;
+static_assert(sizeof(gomel_config) == 72, "gomel_config layout is part of the ABI (ctypes / cgo mirror it)");
+
 enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
                S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_COUNT };
 
@@ -46,10 +63,7 @@ struct gomel_ctx {
     float4* d_tables_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     double* d_tables64 = nullptr;     // strict float64 path (built on first use)
     // mel tables
-    int tbl_mels = 0, tbl_bins = 0;
-    int *d_fwd_lo = nullptr, *d_fwd_hi = nullptr, *d_inv_lo = nullptr, *d_inv_hi = nullptr;
-    float* d_fwd_mod = nullptr;
-    double* d_inv_mod = nullptr;
+    std::vector<MelTables> mel_tabs;      // registered filterbank table sets, most recently used last
     // phase gain tables
     float *d_gain_head = nullptr, *d_gain_mid = nullptr, *d_gain_tail = nullptr;
     long gain_frames_key = -1; double gain_boost_key = 0; int gain_head_len = 0, gain_tail_len = 0;
@@ -75,6 +89,26 @@ int fail(gomel_ctx* c, int code, const std::string& msg)
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? GOMEL_E_NOMEM : GOMEL_E_CUDA,         \
                         std::string(#call) + ": " + cudaGetErrorString(e_));                         \
     } while (0)
+
+// The table set of a config: exact (Resolut, NumMels, MelFmin, MelFmax) match; a config that leaves
+// mel_fmin = mel_fmax = 0 selects the most recently registered set for its (Resolut, NumMels).
+const MelTables* find_mel_tables(gomel_ctx* ctx, const gomel_config* cfg)
+{
+    const bool any = cfg->mel_fmin == 0 && cfg->mel_fmax == 0;
+    for (size_t i = ctx->mel_tabs.size(); i-- > 0;) {
+        const MelTables& t = ctx->mel_tabs[i];
+        if (t.n_fft == cfg->n_fft && t.n_mels == cfg->n_mels && (any || (t.fmin == cfg->mel_fmin && t.fmax == cfg->mel_fmax))) {
+            if (i + 1 != ctx->mel_tabs.size()) {            // most recently used last
+                MelTables m = t;
+                ctx->mel_tabs.erase(ctx->mel_tabs.begin() + (long)i);
+                ctx->mel_tabs.push_back(m);
+            }
+            return &ctx->mel_tabs.back();
+        }
+    }
+    fail(ctx, GOMEL_E_STATE, "mel tables not set for this Resolut / NumMels / MelFmin / MelFmax (gomel_set_mel_tables)");
+    return nullptr;
+}
 
 int ensure(gomel_ctx* ctx, int slot, size_t bytes, void** out)
 {
@@ -238,9 +272,9 @@ int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_si
     p.sig = d_sig; p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
     p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, sig_len);
     if (mode == MODE_MEL) {
-        if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels || cfg->n_fft / 2 != ctx->tbl_bins)
-            return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
-        p.fwd_lo = ctx->d_fwd_lo; p.fwd_hi = ctx->d_fwd_hi; p.fwd_mod = ctx->d_fwd_mod; p.n_mels = cfg->n_mels;
+        const MelTables* mt = find_mel_tables(ctx, cfg);
+        if (!mt) return GOMEL_E_STATE;
+        p.fwd_lo = mt->fwd_lo; p.fwd_hi = mt->fwd_hi; p.fwd_mod = mt->fwd_mod; p.n_mels = cfg->n_mels;
         p.mel_out = d_out;
     } else if (mode == MODE_PHASE) {
         if (cfg->n_freqs <= 0 || cfg->n_freqs > kN / 2) return fail(ctx, GOMEL_E_ARG, "NumFreqs out of range");
@@ -322,18 +356,18 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
 template <typename T>
 int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, float* d_mags)
 {
-    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels || cfg->n_fft / 2 != ctx->tbl_bins)
-        return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
+    const MelTables* mt = find_mel_tables(ctx, cfg);
+    if (!mt) return GOMEL_E_STATE;
     if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
     long g = (n_rows + kMagsRowsPerPass - 1) / kMagsRowsPerPass;
     if (g > 148L * 8) g = 148L * 8;
     const size_t sm = (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double);
     if (cfg->n_fft == 256 * kAltFS)
         k_mags_from_mel<T, kAltFS><<<(unsigned)g, 256, sm, ctx->st>>>(
-            d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+            d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     else
         k_mags_from_mel<T><<<(unsigned)g, 256, sm, ctx->st>>>(
-            d_mel, d_mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+            d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     ctx->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -391,8 +425,8 @@ int from_mel_f64(gomel_ctx* ctx, const gomel_config* cfg, const double* d_mel, l
                  unsigned long long seed, double* h_out)
 {
     using namespace gomel::f64;
-    if (cfg->n_mels <= 0 || cfg->n_mels != ctx->tbl_mels || cfg->n_fft / 2 != ctx->tbl_bins)
-        return fail(ctx, GOMEL_E_STATE, "mel tables not set for this NumMels (gomel_set_mel_tables)");
+    const MelTables* mt = find_mel_tables(ctx, cfg);
+    if (!mt) return GOMEL_E_STATE;
     if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
     const long ola = kN + (n_frames - 1) * (long)kHop;
     if (!ctx->d_tables64) {
@@ -425,7 +459,7 @@ int from_mel_f64(gomel_ctx* ctx, const gomel_config* cfg, const double* d_mel, l
     if (int rc = ensure(ctx, S_MAGS64, (size_t)n_frames * 2049 * 8, &mags)) return rc;
     long g = n_frames < 148L * 8 ? n_frames : 148L * 8;
     k_mags_from_mel_f64<<<(unsigned)g, 256, (size_t)cfg->n_mels * 2 * sizeof(double), ctx->st>>>(
-        d_mel, (double*)mags, ctx->d_inv_lo, ctx->d_inv_hi, ctx->d_inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_frames);
+        d_mel, (double*)mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_frames);
     ctx->launches++;
     if (h_init) CU(cudaMemcpyAsync(sigA, h_init, (size_t)ola * 8, cudaMemcpyHostToDevice, ctx->st));
     else {
@@ -515,8 +549,7 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_tables_alt);
     cudaFree(ctx->d_tables64);
-    cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
-    cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
+    for (MelTables& t : ctx->mel_tabs) t.release();
     cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st_h2d); cudaStreamDestroy(ctx->st_d2h);
@@ -572,22 +605,37 @@ int gomel_set_mel_tables(gomel_ctx* ctx, const gomel_config* cfg, const int* fwd
         if (inv_lo[i] < 0 || (copy && inv_lo[i] >= mels) || (!copy && !lerp && inv_hi[i] > mels))
             return fail(ctx, GOMEL_E_ARG, "inverse mel table indexes outside the mel axis (the Go reference panics)");
     }
+    // kernels already enqueued may still read a set that is replaced or evicted below
     CU(cudaStreamSynchronize(ctx->st));
-    cudaFree(ctx->d_fwd_lo); cudaFree(ctx->d_fwd_hi); cudaFree(ctx->d_fwd_mod);
-    cudaFree(ctx->d_inv_lo); cudaFree(ctx->d_inv_hi); cudaFree(ctx->d_inv_mod);
-    ctx->d_fwd_lo = ctx->d_fwd_hi = ctx->d_inv_lo = ctx->d_inv_hi = nullptr; ctx->d_fwd_mod = nullptr; ctx->d_inv_mod = nullptr;
-    ctx->tbl_mels = ctx->tbl_bins = 0;
+    for (size_t i = 0; i < ctx->mel_tabs.size(); i++) {          // same key: replace
+        MelTables& t = ctx->mel_tabs[i];
+        if (t.n_fft == cfg->n_fft && t.n_mels == mels && t.fmin == cfg->mel_fmin && t.fmax == cfg->mel_fmax) {
+            t.release();
+            ctx->mel_tabs.erase(ctx->mel_tabs.begin() + (long)i);
+            break;
+        }
+    }
+    if (ctx->mel_tabs.size() >= kMaxMelTables) {                 // evict the least recently used set
+        ctx->mel_tabs.front().release();
+        ctx->mel_tabs.erase(ctx->mel_tabs.begin());
+    }
     std::vector<float> fm(mels);
     for (int i = 0; i < mels; i++) fm[i] = (float)fwd_mod[i];
-    CU(cudaMalloc(&ctx->d_fwd_lo, mels * 4)); CU(cudaMalloc(&ctx->d_fwd_hi, mels * 4)); CU(cudaMalloc(&ctx->d_fwd_mod, mels * 4));
-    CU(cudaMalloc(&ctx->d_inv_lo, B * 4)); CU(cudaMalloc(&ctx->d_inv_hi, B * 4)); CU(cudaMalloc(&ctx->d_inv_mod, B * 8));
-    CU(cudaMemcpy(ctx->d_fwd_lo, fwd_lo, mels * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_fwd_hi, fwd_hi, mels * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_fwd_mod, fm.data(), mels * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_inv_lo, inv_lo, B * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_inv_hi, inv_hi, B * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_inv_mod, inv_mod, B * 8, cudaMemcpyHostToDevice));
-    ctx->tbl_mels = mels; ctx->tbl_bins = B;
+    MelTables t;
+    t.n_fft = cfg->n_fft; t.n_mels = mels; t.fmin = cfg->mel_fmin; t.fmax = cfg->mel_fmax;
+    auto upload = [&]() -> int {
+        CU(cudaMalloc(&t.fwd_lo, mels * 4)); CU(cudaMalloc(&t.fwd_hi, mels * 4)); CU(cudaMalloc(&t.fwd_mod, mels * 4));
+        CU(cudaMalloc(&t.inv_lo, B * 4)); CU(cudaMalloc(&t.inv_hi, B * 4)); CU(cudaMalloc(&t.inv_mod, B * 8));
+        CU(cudaMemcpy(t.fwd_lo, fwd_lo, mels * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t.fwd_hi, fwd_hi, mels * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t.fwd_mod, fm.data(), mels * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t.inv_lo, inv_lo, B * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t.inv_hi, inv_hi, B * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t.inv_mod, inv_mod, B * 8, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (int rc = upload()) { t.release(); return rc; }
+    ctx->mel_tabs.push_back(t);
     return 0;
 }
 

@@ -8,8 +8,11 @@
 #pragma once
 #include <array>
 #include <cmath>
+#include <mutex>
 #include <random>
+#include <set>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -52,7 +55,22 @@ struct Mel {                                         // mel/mel.go:10-27
         gomel_config c{};
         c.n_fft = Resolut; c.hop = Window; c.n_mels = NumMels; c.gl_iters = GriffinLimIterations;
         c.tune_mul = TuneMul; c.tune_add = TuneAdd; c.volume_boost = VolumeBoost;
+        c.mel_fmin = MelFmin; c.mel_fmax = MelFmax;        // key of this object's filterbank tables
         return c;
+    }
+
+    // Registers this configuration's tables once per process (the library keeps them by key, so Mel objects with
+    // different configurations can share the context from different threads); `force` after GOMEL_E_STATE.
+    Error use_tables(gomel_ctx* ctx, const gomel_config& cfg, bool force = false) const
+    {
+        static std::mutex mu;
+        static std::set<std::tuple<int, int, double, double>> done;
+        const auto key = std::make_tuple(Resolut, NumMels, MelFmin, MelFmax);
+        std::lock_guard<std::mutex> g(mu);
+        if (!force && done.count(key)) return "";
+        Error e = set_tables(ctx, cfg);
+        if (e.empty()) { if (done.size() >= 48) done.clear(); done.insert(key); }
+        return e;
     }
 
     // the (int(inlo), int(inhi), modlo) triples of domel / undomel, mel/impl.go:313-323, :350-360
@@ -90,9 +108,12 @@ struct Mel {                                         // mel/mel.go:10-27
         const gomel_config cfg = config();
         long np = 0, frames = 0, ola = 0;
         if (gomel_frames(&cfg, (long)buf.size(), &np, &frames, &ola)) return { {}, "bad length" };
-        if (!(err = set_tables(ctx, cfg)).empty()) return { {}, err };
+        if (!(err = use_tables(ctx, cfg)).empty()) return { {}, err };
         std::vector<Pair> out((size_t)frames * NumMels);
-        if (gomel_to_mel(ctx, &cfg, buf.data(), (long)buf.size(), &out[0][0])) return { {}, gomel_last_error(ctx) };
+        int rc = gomel_to_mel(ctx, &cfg, buf.data(), (long)buf.size(), &out[0][0]);
+        if (rc == GOMEL_E_STATE && use_tables(ctx, cfg, true).empty())      // set evicted meanwhile
+            rc = gomel_to_mel(ctx, &cfg, buf.data(), (long)buf.size(), &out[0][0]);
+        if (rc) return { {}, gomel_last_error(ctx) };
         return { std::move(out), "" };
     }
 
@@ -106,7 +127,7 @@ struct Mel {                                         // mel/mel.go:10-27
         const gomel_config cfg = config();
         if (NumMels <= 0 || ospectrum.empty() || ospectrum.size() % (size_t)NumMels)
             return { {}, "len(ospectrum) is not a multiple of NumMels (the Go reference panics)" };
-        if (!(err = set_tables(ctx, cfg)).empty()) return { {}, err };
+        if (!(err = use_tables(ctx, cfg)).empty()) return { {}, err };
         const long frames = (long)(ospectrum.size() / NumMels);
         const long ola = Resolut + (frames - 1) * (long)Window;
         std::vector<double> init = InitSignal;
@@ -118,7 +139,9 @@ struct Mel {                                         // mel/mel.go:10-27
         }
         if ((long)init.size() != ola) return { {}, "InitSignal length != ola_len" };
         std::vector<double> out((size_t)ola);
-        const int rc = gomel_from_mel(ctx, &cfg, &ospectrum[0][0], frames, init.data(), 0, out.data());
+        int rc = gomel_from_mel(ctx, &cfg, &ospectrum[0][0], frames, init.data(), 0, out.data());
+        if (rc == GOMEL_E_STATE && use_tables(ctx, cfg, true).empty())
+            rc = gomel_from_mel(ctx, &cfg, &ospectrum[0][0], frames, init.data(), 0, out.data());
         for (auto& p : ospectrum) { p[0] = std::exp(p[0]); p[1] = std::exp(p[1]); }
         if (rc) return { {}, gomel_last_error(ctx) };
         return { std::move(out), "" };

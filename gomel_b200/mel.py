@@ -54,7 +54,7 @@ class Mel:
 
     def _ctx(self, cfg):
         ctx = _lib.default_context(self.Device)
-        ctx.set_mel_tables(cfg, self.MelFmin, self.MelFmax)
+        ctx.use_mel_tables(cfg, self.MelFmin, self.MelFmax)     # keyed: safe when Mel objects share the context
         return ctx
 
     # ---- buffer API

@@ -49,6 +49,9 @@ typedef struct {
     double tune_add;     /* TuneAdd */
     double volume_boost; /* VolumeBoost (phase: multiplicative, applied iff != 0) */
     int flags;           /* GOMEL_FLAG_* */
+    double mel_fmin;     /* MelFmin, MelFmax: with (n_fft, n_mels) the KEY of the filterbank tables registered by */
+    double mel_fmax;     /* gomel_set_mel_tables -- never evaluated by the library.  Both 0: the most recently
+                            registered tables for this (n_fft, n_mels). */
 } gomel_config;
 
 /* STRICT mode for gomel_from_mel: the whole Griffin-Lim loop in float64 (kernels_f64.cuh).  Griffin-Lim is
@@ -75,7 +78,10 @@ long gomel_ola_len(const gomel_config *cfg, long n_frames);
  * The per-band values domel (mel/impl.go:313-323) and undomel (:350-360) derive: int(inlo),
  * int(inhi), modlo.  Computed by the CALLER's math library (Go's math.Exp/Log in the cgo
  * binding) because two edges are 1-ulp fragile (SURVEY.md hard part 4); the library never
- * evaluates exp/log for table construction.  fwd_*: n_mels entries; inv_*: n_fft/2 entries. */
+ * evaluates exp/log for table construction.  fwd_*: n_mels entries; inv_*: n_fft/2 entries.
+ * A context keeps up to 64 table sets keyed by (n_fft, n_mels, mel_fmin, mel_fmax) of `cfg`; the mel
+ * entry points look the set up by the same key of THEIR cfg, so goroutines / threads with different
+ * Mel configurations can share one context (registering a key again replaces its tables). */
 int  gomel_set_mel_tables(gomel_ctx *ctx, const gomel_config *cfg,
                           const int *fwd_lo, const int *fwd_hi, const double *fwd_mod,
                           const int *inv_lo, const int *inv_hi, const double *inv_mod);

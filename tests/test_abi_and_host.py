@@ -53,9 +53,10 @@ def test_mel_tables_match_oracle(lib, oracle):
 
 
 def test_config_struct_layout_matches_header(lib):
-    # int x5, double x3, int: natural alignment -> 56 bytes on LP64
-    assert C.sizeof(lib.Config) == 56
+    # int x5, double x3, int, double x2: natural alignment -> 72 bytes on LP64
+    assert C.sizeof(lib.Config) == 72
     assert lib.Config.tune_mul.offset == 24 and lib.Config.flags.offset == 48
+    assert lib.Config.mel_fmin.offset == 56 and lib.Config.mel_fmax.offset == 64
 
 
 def test_no_gpu_means_loud_failure(lib):
@@ -65,10 +66,12 @@ def test_no_gpu_means_loud_failure(lib):
     code = ("import sys; sys.path.insert(0, %r)\n"
             "from gomel_b200 import _lib\n"
             "try:\n    _lib.Context(0)\n    print('CTX')\n"
-            "except _lib.GomelError as e:\n    print('RAISED', e.code)\n") % ROOT
+            "except _lib.GomelError as e:\n    print('RAISED', e.code)\n"
+            "try:\n    _lib.default_context(0)\n    print('CTX')\n"
+            "except _lib.GomelError as e:\n    print('RAISED2', e.code)\n") % ROOT
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env).stdout
-    assert "RAISED" in out
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120).stdout
+    assert "RAISED" in out and "RAISED2" in out and "CTX" not in out
 
 
 def test_product_does_not_import_oracle():
