@@ -344,9 +344,8 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
     CU(cudaEventRecord(ctx->ev_k1, ctx->st));
     ctx->hot_launches = iters;
     if (p.tl.n_tiles > 1) {
-        const long total = (long)(p.tl.n_tiles - 1) * geo.halo * n_clips;
-        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, geo.hop, geo.halo,
-                                                           n_clips, 0, 1, p.hb_tiles, p);
+        k_halo_fix<<<(unsigned)(grid - n_clips), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, geo.hop,
+                                                                  geo.halo, 0, 1, p.hb_tiles, p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -411,9 +410,8 @@ int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_
     k_istft_phase<kHS><<<(unsigned)grid, kThreads, kFwdSmemBytes, ctx->st>>>(p);
     ctx->launches++;
     if (p.tl.n_tiles > 1) {
-        const long total = (long)(p.tl.n_tiles - 1) * kHalo * n_clips;
-        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(d_out, (const float*)hb, p.tl, kHop, kHalo, n_clips, 1, 1,
-                                                           p.hb_tiles, p);
+        k_halo_fix<<<(unsigned)(grid - n_clips), 256, 0, ctx->st>>>(d_out, (const float*)hb, p.tl, kHop, kHalo, 1, 1,
+                                                                  p.hb_tiles, p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -1275,9 +1273,8 @@ int gomel_ts_finish(gomel_ts* ts, int iters, float* d_out_local)
     const int t_first = ts->ext_prev ? 0 : 1;
     if (iters > 0 && ts->tl.n_tiles - t_first > 0) {
         SynParams p = {};
-        const long total = (long)(ts->tl.n_tiles - t_first) * kHalo;
-        k_halo_fix<<<grid_1d(total, 256), 256, 0, ctx->st>>>(fin, ts->hb[(iters - 1) & 1], ts->tl, kHop, kHalo, 1, 0, t_first,
-                                                           ts->tl.n_tiles + 1, p);
+        k_halo_fix<<<(unsigned)(ts->tl.n_tiles - t_first), 256, 0, ctx->st>>>(fin, ts->hb[(iters - 1) & 1], ts->tl, kHop, kHalo,
+                                                                            0, t_first, ts->tl.n_tiles + 1, p);
         ctx->launches++;
     }
     CU(cudaMemcpyAsync(d_out_local, fin, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));

@@ -175,6 +175,27 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
     for (int j = 0; j < SH; j++) { const long o = (KEEP + j) * 256 + t; nxt[j] = (o < lim) ? __ldg(sig + o) : 0.0f; }
     __syncthreads();
 
+    // MODE_MEL: a thread's mel work items (frame of the pair, mel band) are the same for every pair of the tile;
+    // their band descriptors stay in registers.  Items are ordered widest band first and dealt boustrophedon so
+    // every thread gets about the same number of taps.
+    constexpr int kHoist = 2;                      // rounds covered by registers: NumMels <= 256
+    const int n_items = (MODE == MODE_MEL) ? 2 * p.n_mels : 0;
+    int h_lo[kHoist], h_hi[kHoist], h_out[kHoist];
+    float h_w[kHoist];
+    if (MODE == MODE_MEL) {
+#pragma unroll
+        for (int q = 0; q < kHoist; q++) {
+            const int i = q * kThreads + ((q & 1) ? kThreads - 1 - t : t);
+            h_out[q] = -1; h_lo[q] = h_hi[q] = 0; h_w[q] = 0.0f;
+            if (i < n_items) {
+                const int mel = p.n_mels - 1 - (i >> 1);
+                h_lo[q] = __ldg(p.fwd_lo + mel); h_hi[q] = __ldg(p.fwd_hi + mel);
+                h_w[q] = (h_lo[q] + 1 == h_hi[q]) ? __ldg(p.fwd_mod + mel) : 1.0f / (float)(h_hi[q] - h_lo[q] + 1);
+                h_out[q] = (i & 1) * p.n_mels + mel;
+            }
+        }
+    }
+
     for (int pr = 0; pr < npairs; pr++) {
         const long off0 = (long)pr * 2 * H;
 #pragma unroll
@@ -244,22 +265,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
             // domel (mel/impl.go:310-345): one work item = (frame, mel), both channels in one pass over the band:
             // ch0 sums |X[k]| for k in [lo,hi), ch1 sums |X[N-1-k]| = |X[k+1]| for the same k.  Items are ordered
             // widest band first and dealt boustrophedon so every thread gets about the same number of taps.
-            const int n_items = 2 * p.n_mels;
             float2* outp = reinterpret_cast<float2*>(p.mel_out) + ((long)clip * p.tl.n_frames + fA) * p.n_mels;
-            for (int q = 0; q * kThreads < n_items; q++) {
-                const int i = q * kThreads + ((q & 1) ? kThreads - 1 - t : t);
-                if (i >= n_items) continue;
-                const int fr = i & 1, mel = p.n_mels - 1 - (i >> 1);
-                if (fr == 1 && !validB) continue;
+            auto do_item = [&](int o, int lo, int hi, float w) {       // o = fr * n_mels + mel
+                const int fr = o >= p.n_mels;
+                if (fr == 1 && !validB) return;
                 const float* S = fr ? SB : SA;
-                const int lo = p.fwd_lo[mel], hi = p.fwd_hi[mel];
                 float t0 = 0.0f, t1 = 0.0f;
-                if (lo + 1 == hi) {
-                    const float md = p.fwd_mod[mel];
+                if (lo + 1 == hi) {                                  // w = modlo
                     const float s0 = S[lo + (lo >> 4)], s1 = S[hi + (hi >> 4)], s2 = S[hi + 1 + ((hi + 1) >> 4)];
-                    t0 = s0 * (1.0f - md); t0 += s1 * md;
-                    t1 = s1 * (1.0f - md); t1 += s2 * md;
-                } else if (hi > lo) {
+                    t0 = s0 * (1.0f - w); t0 += s1 * w;
+                    t1 = s1 * (1.0f - w); t1 += s2 * w;
+                } else if (hi > lo) {                                // w = 1 / (count + 1)
+#ifndef GOMEL_EXP_NOBAND
                     int idx = lo + (lo >> 4);
                     float prev = S[idx];
                     for (int k = lo; k < hi; k++) {          // prev = S[k]; next = S[k+1]
@@ -268,12 +285,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
                         t0 += prev; t1 += nextv;
                         prev = nextv;
                     }
-                    const float inv = 1.0f / (float)(hi - lo + 1);
-                    t0 *= inv; t1 *= inv;
+#else
+                    t0 = S[lo + (lo >> 4)]; t1 = S[hi + (hi >> 4)];
+#endif
+                    t0 *= w; t1 *= w;
                 }
                 t0 = (t0 < 1e-5f) ? 1e-5f : t0;
                 t1 = (t1 < 1e-5f) ? 1e-5f : t1;
-                outp[(long)fr * p.n_mels + mel] = make_float2(logf(t0), logf(t1));
+                outp[o] = make_float2(logf(t0), logf(t1));
+            };
+#pragma unroll
+            for (int q = 0; q < kHoist; q++)
+                if (h_out[q] >= 0) do_item(h_out[q], h_lo[q], h_hi[q], h_w[q]);
+            for (int q = kHoist; q * kThreads < n_items; q++) {      // NumMels > 256 only
+                const int i = q * kThreads + ((q & 1) ? kThreads - 1 - t : t);
+                if (i >= n_items) continue;
+                const int mel = p.n_mels - 1 - (i >> 1);
+                const int lo = p.fwd_lo[mel], hi = p.fwd_hi[mel];
+                do_item((i & 1) * p.n_mels + mel, lo, hi, (lo + 1 == hi) ? p.fwd_mod[mel] : 1.0f / (float)(hi - lo + 1));
             }
         } else if (MODE == MODE_PHASE) {
             float2* SA = stg;
@@ -747,24 +776,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
 }
 
 // finishes the samples shared by two tiles: sig[s] = (sig[s] + hb[s]) * gain, for the head regions of
-// tiles t_first .. n_tiles-1 (t_first = 0 when a previous rank's tail partial sits in sig[0..halo))
+// tiles t_first .. n_tiles-1 (t_first = 0 when a previous rank's tail partial sits in sig[0..halo)).
+// One CTA per (clip, tile) head region: no per-element index arithmetic.
 __global__ void k_halo_fix(float* __restrict__ sig, const float* __restrict__ hb, Tiling tl, int hop, int halo,
-                           int n_clips, int use_gain, int t_first, int hb_tiles, SynParams gp)
+                           int use_gain, int t_first, int hb_tiles, SynParams gp)
 {
-    const long per_clip = (long)(tl.n_tiles - t_first) * halo;
-    const long total = per_clip * n_clips;
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long step = (long)gridDim.x * blockDim.x;
-    for (; i < total; i += step) {
-        const int clip = (int)(i / per_clip);
-        const long r = i - (long)clip * per_clip;
-        const int tile = (int)(r / halo) + t_first, o = (int)(r % halo);
-        const long s_abs = (long)tile_begin(tl, tile) * hop + o;
-        if (s_abs >= tl.sig_len) continue;
-        float* d = sig + (long)clip * tl.sig_stride + s_abs;
-        float x = *d + hb[((long)clip * hb_tiles + tile) * halo + o];
-        if (use_gain) x *= gain_at(gp, s_abs, (int)(s_abs % hop));
-        *d = x;
+    const int nt = tl.n_tiles - t_first;
+    const int clip = blockIdx.x / nt, tile = blockIdx.x % nt + t_first;
+    const long s0 = (long)tile_begin(tl, tile) * hop;            // a multiple of hop
+    float* __restrict__ d = sig + (long)clip * tl.sig_stride + s0;
+    const float* __restrict__ h = hb + ((long)clip * hb_tiles + tile) * halo;
+    const long room = tl.sig_len - s0;
+    const int n = (int)(room < halo ? (room < 0 ? 0 : room) : halo);
+    for (int o = threadIdx.x; o < n; o += blockDim.x) {
+        float x = d[o] + h[o];
+        if (use_gain) x *= gain_at(gp, s0 + o, o % hop);
+        d[o] = x;
     }
 }
 
