@@ -278,10 +278,25 @@ def run_product(args):
     barrier()
     checksum = float(np.abs(h_out[:: max(1, clips // 8), ::4099]).sum())
 
+    # ---- the same end-to-end call with 16-bit PCM output (what cmd/towav writes): half the D2H bytes
+    h_pcm, h_pcm_owner = ctx.pinned_array((clips, ola), np.int16)
+
+    def step_pcm(seed):
+        ctx.check(ctx.lib.gomel_from_mel_batch_host_pcm16(ctx.h, C.byref(cfg), h_mel.ctypes.data_as(C.c_void_p), clips, frames,
+                                                          None, seed, h_pcm.ctypes.data_as(C.c_void_p), args.chunk))
+    step_pcm(0)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_pcm(3000 + s)
+    ctx.sync()
+    pcm_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
     if use_dist:
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_ms, pcm_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dev_ms, e2e_ms, pcm_ms = float(t[0]), float(t[1]), float(t[2])
 
     audio_s_per_step = world * clips * frames * HOP / SR          # seconds of audio covered by the frames
     value = audio_s_per_step * args.steps / (dev_ms / 1e3)
@@ -308,6 +323,8 @@ def run_product(args):
                         "algorithmic_bytes_per_launch": BYTES_PER_FRAME_ITER * clips * frames,
                         "avg_launch_ms": per_launch_s * 1e3, "launches_timed": hot_n,
                         "kernel_share_of_step": hot_ms / dev_ms,
+                        "launch_note": "one timed launch = one Griffin-Lim iteration over the whole batch, issued as two "
+                                       "concurrent half-batch launches of the kernel (clips split over two streams)",
                         "frame_iterations_per_s_per_gpu": frame_iters * args.steps / (hot_ms / 1e3)}
         cpu = None
         if world == 1:                              # rank 0 at N=1 only
@@ -326,7 +343,10 @@ def run_product(args):
                     "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": e2e_ms / args.steps,
                     "api": "gomel_from_mel_batch_host (pinned host float32 in/out, 3-stream pipeline)",
                     "host_numa_node": numa_node,
-                    "checksum": checksum},
+                    "checksum": checksum,
+                    "pcm16": {"value": audio_s_per_step * args.steps / (pcm_ms / 1e3), "ms_per_step": pcm_ms / args.steps,
+                              "d2h_bytes_per_step": int(h_pcm.nbytes),
+                              "api": "gomel_from_mel_batch_host_pcm16 (int16 PCM out, the sample format of cmd/towav)"}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stft_frames_per_s": frame_iters * world * args.steps / (dev_ms / 1e3),
             "stft_frames_per_s_note": "Griffin-Lim frame-iterations (one analysis STFT + one synthesis ISTFT each) per second, whole job",
@@ -366,6 +386,7 @@ def run_product(args):
     ctx.dev_free(d_out)
     ctx.host_free(h_mel_owner)
     ctx.host_free(h_out_owner)
+    ctx.host_free(h_pcm_owner)
     if rank == 0:
         print(json.dumps(line))
     if use_dist:

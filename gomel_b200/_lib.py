@@ -85,6 +85,7 @@ SIGNATURES = {
     "gomel_ts_run_nccl": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "gomel_copy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "gomel_from_mel_batch_host": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, _vp, C.c_int]),
+    "gomel_from_mel_batch_host_pcm16": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, _vp, C.c_int]),
     "gomel_to_mel_batch_host": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_int]),
 }
 

@@ -67,16 +67,17 @@ def towav_dir(in_dir, out_dir, mel, seed=0, init_signals=None):
         init = None
         if init_signals is not None:
             init = np.stack([init_signals[os.path.basename(g[0])] for g in group]).astype(np.float32)
-        out = np.empty((len(group), ola), np.float32)
-        ctx.check(ctx.lib.gomel_from_mel_batch_host(
+        # the waveforms come back as the 16-bit PCM samples dumpwav would write (quantised on the GPU)
+        out = np.empty((len(group), ola), np.int16)
+        ctx.check(ctx.lib.gomel_from_mel_batch_host_pcm16(
             ctx.h, C.byref(cfg), spec.ctypes.data_as(C.c_void_p), len(group), frames,
             init.ctypes.data_as(C.c_void_p) if init is not None else None, seed, out.ctypes.data_as(C.c_void_p), 0))
         for i, (f, _, samples, sr) in enumerate(group):
-            w = out[i].astype(np.float64)
+            w = out[i]
             if int(samples) > 0 and codec.is_padded(int(samples), len(w), mel.Window) and len(w) > int(samples):
                 w = w[:int(samples)]
             rate = mel.SampleRate if mel.SampleRate else int(sr)
             dst = os.path.join(out_dir, os.path.basename(f) + ".wav")
-            codec.save_wav(dst, w, rate)
+            codec.save_wav_pcm16(dst, w, rate)
             written.append(dst)
     return written

@@ -84,12 +84,16 @@ def load_wav(path):
 def save_wav(path, data, sr):
     """dumpwav (mel/impl.go:195-232): mono 16-bit PCM; beep clamps to [-1,1] and scales by 2^15-1"""
     x = np.clip(np.asarray(data, np.float64), -1.0, 1.0)
-    pcm = (x * 32767.0).astype("<i2")
+    save_wav_pcm16(path, (x * 32767.0).astype("<i2"), sr)
+
+
+def save_wav_pcm16(path, pcm, sr):
+    """The container half of dumpwav for samples already quantised (gomel_from_mel_batch_host_pcm16)."""
     with wave.open(path, "wb") as w:
         w.setnchannels(1)
         w.setsampwidth(2)
         w.setframerate(int(sr) if sr else 44100)
-        w.writeframes(pcm.tobytes())
+        w.writeframes(np.ascontiguousarray(pcm, "<i2").tobytes())
 
 
 # ---------------------------------------------------------------- PNG containers

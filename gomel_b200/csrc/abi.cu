@@ -30,6 +30,7 @@ struct Geo {
     long ola(long n_frames) const { return n_fft + (n_frames - 1) * (long)hop; }
 };
 constexpr int kAltHS = 1, kAltFS = 8;
+constexpr int kGlCtasPerSm = 2;
 
 // One registered set of domel / undomel tables.  Keyed by (Resolut, NumMels, MelFmin, MelFmax) so that callers
 // with different Mel configurations can share a context concurrently (set + compute are two calls).
@@ -49,7 +50,7 @@ constexpr size_t kMaxMelTables = 64;
 static_assert(sizeof(gomel_config) == 72, "gomel_config layout is part of the ABI (ctypes / cgo mirror it)");
 
 enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
-               S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_COUNT };
+               S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_CH6, S_CH7, S_COUNT };
 
 }  // namespace
 
@@ -57,6 +58,11 @@ struct gomel_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
+    // Griffin-Lim batches are split by clip over st + these streams: the iterations of one group of clips only
+    // depend on that group, so the launch tail of one group is covered by the other groups' launches
+    cudaStream_t st_gl[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
+    int gl_streams = 2;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
     float4* d_tables = nullptr;
@@ -331,18 +337,37 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
     if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
     const float* cur = d_init;
     CU(cudaEventRecord(ctx->ev_k0, ctx->st));
+    // groups of clips on concurrent streams (group g: clips [g*n/ns, (g+1)*n/ns)); every group needs whole waves
+    int ns = ctx->gl_streams;
+    while (ns > 1 && grid / ns < (long)kGlCtasPerSm * ctx->sm_count * 2) ns--;
+    if (ns > n_clips) ns = n_clips;
+    cudaStream_t gs[4] = { ctx->st, ctx->st_gl[0], ctx->st_gl[1], ctx->st_gl[2] };
+    if (ns > 1) {
+        CU(cudaEventRecord(ctx->ev_fork, ctx->st));
+        for (int g = 1; g < ns; g++) CU(cudaStreamWaitEvent(gs[g], ctx->ev_fork, 0));
+    }
     for (int i = 0; i < iters; i++) {
         float* dst = (((iters - 1 - i) & 1) == 0) ? d_out : (float*)tmp;
         p.sig_in = cur; p.sig_out = dst;
         p.hb_in = (i == 0) ? nullptr : (const float*)hb[(i - 1) & 1];
         p.hb_out = (float*)hb[i & 1];
-        if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<(unsigned)grid, kThreads, kGlSmemBytes, ctx->st>>>(p);
-        else k_gl_iter<kHS><<<(unsigned)grid, kThreads, kGlSmemBytes, ctx->st>>>(p);
-        ctx->launches++;
+        for (int g = 0; g < ns; g++) {
+            const int c0 = (int)((long)n_clips * g / ns), c1 = (int)((long)n_clips * (g + 1) / ns);
+            p.clip0 = c0;
+            const unsigned gg = (unsigned)((long)(c1 - c0) * p.tl.n_tiles);
+            if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+            else k_gl_iter<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+            ctx->launches++;
+        }
         cur = dst;
     }
+    p.clip0 = 0;
+    for (int g = 1; g < ns; g++) {
+        CU(cudaEventRecord(ctx->ev_join[g - 1], gs[g]));
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_join[g - 1], 0));
+    }
     CU(cudaEventRecord(ctx->ev_k1, ctx->st));
-    ctx->hot_launches = iters;
+    ctx->hot_launches = iters;          // one "launch" = one iteration over the whole batch, whatever the grouping
     if (p.tl.n_tiles > 1) {
         k_halo_fix<<<(unsigned)(grid - n_clips), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, geo.hop,
                                                                   geo.halo, 0, 1, p.hb_tiles, p);
@@ -512,6 +537,15 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         CU(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; i++) {
+            CU(cudaStreamCreateWithFlags(&ctx->st_gl[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("GOMEL_GL_STREAMS")) {           // tuning knob, 1..4
+            const int v = atoi(e);
+            if (v >= 1 && v <= 4) ctx->gl_streams = v;
+        }
         CU(cudaEventCreate(&ctx->ev0));
         CU(cudaEventCreate(&ctx->ev1));
         CU(cudaEventCreate(&ctx->ev_k0));
@@ -551,6 +585,8 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st_h2d); cudaStreamDestroy(ctx->st_d2h);
+    for (int i = 0; i < 3; i++) { cudaStreamDestroy(ctx->st_gl[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -936,11 +972,9 @@ int gomel_from_phase_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d
 
 // ------------------------------------------------------------------- pipelined host batches
 // chunk c uses buffer set c&1; H2D on st_h2d, kernels on st, D2H on st_d2h, ordered by events
-int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
-                              const float* init, unsigned long long seed, float* out, int clips_per_chunk)
+static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
+                                    const float* init, unsigned long long seed, void* out, int clips_per_chunk, bool pcm16)
 {
-    if (!ctx) return GOMEL_E_ARG;
-    Guard g(ctx);
     Geo geo;
     if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     if (!mel || !out || n_clips <= 0 || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
@@ -948,11 +982,12 @@ int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const flo
     const long mel_per = n_frames * 2L * cfg->n_mels;
     int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
     if (cpc > n_clips) cpc = n_clips;
-    void *dmel[2], *dinit[2] = { nullptr, nullptr }, *dout[2];
+    void *dmel[2], *dinit[2] = { nullptr, nullptr }, *dout[2], *dpcm[2] = { nullptr, nullptr };
     for (int b = 0; b < 2; b++) {
         if (int rc = ensure(ctx, S_CH0 + b, (size_t)cpc * mel_per * 4, &dmel[b])) return rc;
         if (int rc = ensure(ctx, S_CH2 + b, (size_t)cpc * ola * 4, &dout[b])) return rc;
         if (init) { if (int rc = ensure(ctx, S_CH4 + b, (size_t)cpc * ola * 4, &dinit[b])) return rc; }
+        if (pcm16) { if (int rc = ensure(ctx, S_CH6 + b, (size_t)cpc * ola * 2, &dpcm[b])) return rc; }
     }
     cudaEvent_t up[2], done[2], down[2];
     for (int b = 0; b < 2; b++) {
@@ -991,9 +1026,16 @@ int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const flo
         if (c >= 2) cudaStreamWaitEvent(ctx->st, down[b], 0);            // output buffer of chunk c-2 drained
         rc = from_mel_dev_impl<float>(ctx, cfg, (const float*)dmel[b], nc, n_frames, (const float*)dinit[b],
                                       seed + (unsigned long long)c0, ola, (float*)dout[b]);
+        if (pcm16 && !rc) {
+            k_f32_to_pcm16<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st>>>((const float*)dout[b], (short*)dpcm[b], (long)nc * ola);
+            ctx->launches++;
+        }
         cudaEventRecord(done[b], ctx->st);
         cudaStreamWaitEvent(ctx->st_d2h, done[b], 0);
-        cudaMemcpyAsync(out + (size_t)c0 * ola, dout[b], (size_t)nc * ola * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
+        if (pcm16)
+            cudaMemcpyAsync((short*)out + (size_t)c0 * ola, dpcm[b], (size_t)nc * ola * 2, cudaMemcpyDeviceToHost, ctx->st_d2h);
+        else
+            cudaMemcpyAsync((float*)out + (size_t)c0 * ola, dout[b], (size_t)nc * ola * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
         cudaEventRecord(down[b], ctx->st_d2h);
     }
     cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_d2h);
@@ -1001,6 +1043,22 @@ int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const flo
     if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
+}
+
+int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
+                              const float* init, unsigned long long seed, float* out, int clips_per_chunk)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return from_mel_batch_host_impl(ctx, cfg, mel, n_clips, n_frames, init, seed, out, clips_per_chunk, false);
+}
+
+int gomel_from_mel_batch_host_pcm16(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
+                                    const float* init, unsigned long long seed, short* out, int clips_per_chunk)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    return from_mel_batch_host_impl(ctx, cfg, mel, n_clips, n_frames, init, seed, out, clips_per_chunk, true);
 }
 
 int gomel_to_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float* wav, int n_clips, long n_samples,

@@ -74,6 +74,19 @@ __global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ 
     const long step = (long)gridDim.x * blockDim.x;
     for (; i < n; i += step) out[i] = (double)in[i] * scale;
 }
+// 16-bit PCM samples as dumpwav writes them (mel/impl.go:195-232 -> beep wav.Encode, Precision 2): clamp to
+// [-1, 1], scale by 2^15 - 1 in float64, convert like Go's int16() (truncation; NaN -> 0)
+__global__ void k_f32_to_pcm16(const float* __restrict__ in, short* __restrict__ out, long n)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        double v = (double)in[i];
+        if (v < -1.0) v = -1.0;
+        if (v > 1.0) v = 1.0;
+        out[i] = (v == v) ? (short)__double2int_rz(__dmul_rn(v, 32767.0)) : (short)0;
+    }
+}
 // counter-based U[0,1) fill for the Griffin-Lim start signal when the caller injects none
 // (mel/mel.go:80-83 draws rand.Float64(); same distribution, not bit-compatible with math/rand)
 __global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long long seed, long index_offset = 0)
@@ -427,6 +440,7 @@ struct SynParams {
     int tile_lo, tiles_in_launch;     // this launch covers tiles [tile_lo, tile_lo + tiles_in_launch)
     int edge_mode, edge_tile0, edge_tile1;   // edge_mode: grid = 1 or 2 CTAs mapped to these tiles
     int ext_prev, ext_next;  // a previous / next rank continues the clip beyond this buffer
+    int clip0;               // first clip of this launch (a batch is split over concurrent streams by clip)
 };
 
 __device__ __forceinline__ float rsqrt_fast(float x)       // one MUFU.RSQ; callers guarantee x >= 1e-36 (no denormal path)
@@ -470,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     constexpr int NR = FS + HS, SH = 2 * HS, KEEP = FS - HS, H = 256 * HS, HALO = KEEP * 256;
     int tile, clip;
     if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
-    else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = blockIdx.x / p.tiles_in_launch; }
+    else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = p.clip0 + blockIdx.x / p.tiles_in_launch; }
     const int f0 = tile_begin(p.tl, tile);
     const int nf = tile_begin(p.tl, tile + 1) - f0;
     const int npairs = (nf + 1) >> 1;

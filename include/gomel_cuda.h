@@ -206,6 +206,12 @@ int  gomel_ts_run_nccl(gomel_ts *ts, int first_iter, int n_iters, int overlap);
 int  gomel_from_mel_batch_host(gomel_ctx *ctx, const gomel_config *cfg, const float *mel, int n_clips,
                                long n_frames, const float *init, unsigned long long seed, float *out,
                                int clips_per_chunk);
+/* Same pipeline, output as the 16-bit PCM samples dumpwav writes (mel/impl.go:195-232: beep wav.Encode with
+ * Precision 2 clamps to [-1,1] and converts int16(v * 32767)): out: int16 [n_clips][ola_len].  What cmd/towav
+ * ends in; halves the device-to-host traffic of the float32 form. */
+int  gomel_from_mel_batch_host_pcm16(gomel_ctx *ctx, const gomel_config *cfg, const float *mel, int n_clips,
+                                     long n_frames, const float *init, unsigned long long seed, short *out,
+                                     int clips_per_chunk);
 /* wav: [n_clips][n_samples] -> mel_out: [n_clips][n_frames*n_mels*2] */
 int  gomel_to_mel_batch_host(gomel_ctx *ctx, const gomel_config *cfg, const float *wav, int n_clips,
                              long n_samples, float *mel_out, int clips_per_chunk);

@@ -285,6 +285,24 @@ def test_batch_from_mel_matches_single(mctx, lib, oracle):
         assert rel_l2(out[c], refs[c]) < TOL_GL
 
 
+def test_batch_from_mel_pcm16_is_the_wav_quantisation_of_the_float_output(mctx, lib):
+    """gomel_from_mel_batch_host_pcm16 == dumpwav's int16(clamp(v) * 32767) (mel/impl.go:195-232) of the float32 form"""
+    cfg = mel_cfg(lib, iters=2)
+    n_clips, frames = 6, 9
+    ola = 4096 + (frames - 1) * 1280
+    rng = np.random.default_rng(77)
+    mel32 = rng.uniform(-9.0, 2.5, (n_clips, frames * 192, 2)).astype(np.float32)
+    mel32[0] += 3.0                                             # loud clip: samples beyond [-1, 1] get clamped
+    init32 = rng.random((n_clips, ola)).astype(np.float32)
+    f32 = np.empty((n_clips, ola), np.float32)
+    pcm = np.empty((n_clips, ola), np.int16)
+    args = (mel32.ctypes.data_as(C.c_void_p), n_clips, frames, init32.ctypes.data_as(C.c_void_p), 0)
+    mctx.check(mctx.lib.gomel_from_mel_batch_host(mctx.h, C.byref(cfg), *args, f32.ctypes.data_as(C.c_void_p), 4))
+    mctx.check(mctx.lib.gomel_from_mel_batch_host_pcm16(mctx.h, C.byref(cfg), *args, pcm.ctypes.data_as(C.c_void_p), 4))
+    want = (np.clip(f32.astype(np.float64), -1.0, 1.0) * 32767.0).astype(np.int16)     # astype truncates like Go's int16()
+    assert np.abs(f32[0]).max() > 1.0 and np.array_equal(pcm, want)
+
+
 def test_batch_to_mel_matches_oracle(mctx, lib, oracle):
     cfg = mel_cfg(lib)
     n_clips, n = 7, 30000
