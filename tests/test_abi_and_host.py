@@ -195,3 +195,17 @@ def test_png16_reader_handles_all_filter_types(tmp_path):
                  + chunk(b"IDAT", zlib.compress(bytes(out))) + chunk(b"IEND", b""))
     back = codec.read_png(f)
     assert back.dtype == np.uint16 and np.array_equal(back, px)
+
+
+def test_save_wav_pcm16_is_the_container_half_of_save_wav(tmp_path):
+    """codec.save_wav = dumpwav's clamp + int16(v * 32767) (mel/impl.go:195-232) followed by save_wav_pcm16"""
+    from gomel_b200 import codec
+    x = np.concatenate([np.linspace(-1.5, 1.5, 4001), [0.0, 1e-9, -1e-9, 0.99999, -0.99999]])
+    a, b = str(tmp_path / "a.wav"), str(tmp_path / "b.wav")
+    codec.save_wav(a, x, 22050)
+    pcm = (np.clip(x, -1.0, 1.0) * 32767.0).astype(np.int16)          # truncation toward zero, like Go's int16()
+    codec.save_wav_pcm16(b, pcm, 22050)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    y, sr = codec.load_wav(a)
+    assert sr == 22050 and len(y) == len(x) and y[0] == -1.0 and pcm[0] == -32767 and pcm[-1] == -32766
+    assert pcm[-4] == 0 and pcm[-3] == 0                                  # +-1e-9 truncate toward zero
