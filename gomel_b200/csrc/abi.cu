@@ -77,6 +77,7 @@ struct gomel_ctx {
     size_t scratch_cap[S_COUNT] = {};
     unsigned long long launches = 0;
     int tile_override = 0;
+    int gl_tile_waves = 4;            // Griffin-Lim: CTA waves per iteration the automatic tiling aims at
     std::string err;
     std::mutex mu;
 };
@@ -151,7 +152,10 @@ long pad_len(long n, int filter)            // mel/impl.go:429-455
 }
 
 // t_floor: a tile must be at least as long as the halo (samples are shared by at most two tiles)
-Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len, int t_floor = 4)
+// waves: CTA waves per launch the automatic tiling aims at.  Single launches (forward / phase kernels) want
+// many short waves (small tail); Griffin-Lim iterations run as two interleaved groups that cover each other's
+// tails, so they take longer tiles (less per-tile prologue)
+Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len, int t_floor = 4, int waves = 8)
 {
     Tiling tl;
     tl.n_frames = (int)n_frames;
@@ -159,7 +163,7 @@ Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, 
     if (ctx->tile_override > 0) T = ctx->tile_override;
     else {
         const long slots = 2L * ctx->sm_count;
-        long tiles_wanted = (8 * slots + n_clips - 1) / n_clips;
+        long tiles_wanted = (waves * slots + n_clips - 1) / n_clips;
         if (tiles_wanted < 1) tiles_wanted = 1;
         T = (int)((n_frames + tiles_wanted - 1) / tiles_wanted);
         // small batches are latency bound: allow tiles down to 4 frames until every CTA slot has a tile;
@@ -325,7 +329,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
     }
     SynParams p = {};
     p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
-    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4);
+    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves);
     p.mags = d_mags;
     void *tmp = nullptr, *hb[2] = { nullptr, nullptr };
     if (iters > 1) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &tmp)) return rc; }
@@ -339,7 +343,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
     CU(cudaEventRecord(ctx->ev_k0, ctx->st));
     // groups of clips on concurrent streams (group g: clips [g*n/ns, (g+1)*n/ns)); every group needs whole waves
     int ns = ctx->gl_streams;
-    while (ns > 1 && grid / ns < (long)kGlCtasPerSm * ctx->sm_count * 2) ns--;
+    while (ns > 1 && grid / ns < (long)kGlCtasPerSm * ctx->sm_count) ns--;
     if (ns > n_clips) ns = n_clips;
     cudaStream_t gs[4] = { ctx->st, ctx->st_gl[0], ctx->st_gl[1], ctx->st_gl[2] };
     if (ns > 1) {
@@ -542,6 +546,10 @@ int gomel_ctx_create(int device, gomel_ctx** out)
             CU(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("GOMEL_TILE_WAVES")) {           // tuning knob, 1..64
+            const int v = atoi(e);
+            if (v >= 1 && v <= 64) ctx->gl_tile_waves = v;
+        }
         if (const char* e = getenv("GOMEL_GL_STREAMS")) {           // tuning knob, 1..4
             const int v = atoi(e);
             if (v >= 1 && v <= 4) ctx->gl_streams = v;
