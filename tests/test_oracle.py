@@ -75,6 +75,28 @@ def test_c_vs_numpy_mel(oracle):
     assert rel_l2(a, b) < 1e-12                                          # full-spectrum loop == Hermitian form
 
 
+def test_both_restatements_agree_on_the_newmel_default_geometry(oracle):
+    """mel.NewMel() defaults (mel/mel.go:30-41): 160 mels, fmax 8000, Window 256, Resolut 2048, 2 iterations"""
+    from oracle import oracle_np as ONP
+    wav = synth_clip(3, 0.35)
+    cfg = oracle.config(num_mels=160, window=256, resolut=2048, mel_fmax=8000.0, gl_iters=2)
+    a = oracle.to_mel(cfg, wav)
+    b = ONP.to_mel(wav, mels=160, fmax=8000.0, hop=256, N=2048)
+    assert a.shape == b.shape and rel_l2(a, b) < 1e-12
+    frames = len(a) // 160
+    init = np.random.default_rng(6).random(2048 + (frames - 1) * 256)
+    x = oracle.from_mel(cfg, a, init)
+    y = ONP.from_mel(a, init, 2, mels=160, fmax=8000.0, hop=256, N=2048)
+    assert x.shape == y.shape and rel_l2(x, y) < 1e-12
+    # the filterbank tables of the product-side mirror at this geometry == the oracle's
+    from gomel_b200 import _lib
+    flo, fhi, fmod, ilo, ihi, imod = _lib.mel_tables(1024, 160, 0.0, 8000.0)
+    lo, hi, mod = oracle.mel_fwd_tables(1024, 160, 0.0, 8000.0)
+    assert np.array_equal(flo, lo) and np.array_equal(fhi, hi) and np.array_equal(fmod, mod)
+    lo, hi, mod = oracle.mel_inv_tables(1024, 160, 0.0, 8000.0)
+    assert np.array_equal(ilo, lo) and np.array_equal(ihi, hi) and np.array_equal(imod, mod)
+
+
 def test_c_vs_numpy_phase(oracle):
     from oracle import oracle_np as ONP
     wav = synth_clip(1, 0.9)
