@@ -382,6 +382,9 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
 {
     extern __shared__ double e[];     // [kMagsRowsPerPass][n_mels][2]
     const int per_row = 2 * n_mels;
+    // (v - TuneAdd) / TuneMul / N as one multiplication: exact for the default TuneMul = 1, otherwise within one
+    // float64 ulp of the reference's division, far below the float32 rounding of the stored magnitude
+    const double scale = (1.0 / tune_mul) * (1.0 / (256.0 * FS));
     for (long row0 = (long)blockIdx.x * kMagsRowsPerPass; row0 < n_rows; row0 += (long)gridDim.x * kMagsRowsPerPass) {
         const int nr = (int)((n_rows - row0 < kMagsRowsPerPass) ? n_rows - row0 : kMagsRowsPerPass);
         const T* m = mel + row0 * per_row;
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                         for (int k = lo; k < hi; k++) total += er[2 * k + l];
                         total /= (double)(hi - lo + 1);
                     }
-                    const double v = fabs((total - tune_add) / tune_mul) * (1.0 / (256.0 * FS));
+                    const double v = fabs((total - tune_add) * scale);
                     out[l ? 2048 : pos] = (float)v;
                 }
             }
