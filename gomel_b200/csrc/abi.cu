@@ -50,7 +50,7 @@ constexpr size_t kMaxMelTables = 64;
 static_assert(sizeof(gomel_config) == 72, "gomel_config layout is part of the ABI (ctypes / cgo mirror it)");
 
 enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
-               S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_CH6, S_CH7, S_COUNT };
+               S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_CH6, S_CH7, S_PM0, S_PM1, S_PI0, S_PI1, S_COUNT };
 
 }  // namespace
 
@@ -62,6 +62,7 @@ struct gomel_ctx {
     // depend on that group, so the launch tail of one group is covered by the other groups' launches
     cudaStream_t st_gl[3] = { nullptr, nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
+    cudaStream_t st_pre = nullptr;    // batch pipeline: magnitudes / start signal of the next chunk, beside the iterations
     int gl_streams = 2;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
@@ -382,8 +383,9 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_c
 }
 
 template <typename T>
-int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, float* d_mags)
+int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, float* d_mags, cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = ctx->st;
     const MelTables* mt = find_mel_tables(ctx, cfg);
     if (!mt) return GOMEL_E_STATE;
     if (cfg->tune_mul == 0) return fail(ctx, GOMEL_E_ARG, "TuneMul == 0");
@@ -391,10 +393,10 @@ int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_row
     if (g > 148L * 8) g = 148L * 8;
     const size_t sm = (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double);
     if (cfg->n_fft == 256 * kAltFS)
-        k_mags_from_mel<T, kAltFS><<<(unsigned)g, 256, sm, ctx->st>>>(
+        k_mags_from_mel<T, kAltFS><<<(unsigned)g, 256, sm, stream>>>(
             d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     else
-        k_mags_from_mel<T><<<(unsigned)g, 256, sm, ctx->st>>>(
+        k_mags_from_mel<T><<<(unsigned)g, 256, sm, stream>>>(
             d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -546,6 +548,7 @@ int gomel_ctx_create(int device, gomel_ctx** out)
             CU(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&ctx->st_pre, cudaStreamNonBlocking));
         if (const char* e = getenv("GOMEL_TILE_WAVES")) {           // tuning knob, 1..64
             const int v = atoi(e);
             if (v >= 1 && v <= 64) ctx->gl_tile_waves = v;
@@ -595,6 +598,7 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st_h2d); cudaStreamDestroy(ctx->st_d2h);
     for (int i = 0; i < 3; i++) { cudaStreamDestroy(ctx->st_gl[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
+    cudaStreamDestroy(ctx->st_pre);
     delete ctx;
 }
 
@@ -990,18 +994,24 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
     const long mel_per = n_frames * 2L * cfg->n_mels;
     int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
     if (cpc > n_clips) cpc = n_clips;
-    void *dmel[2], *dinit[2] = { nullptr, nullptr }, *dout[2], *dpcm[2] = { nullptr, nullptr };
+    if (cfg->gl_iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
+    void *dmel[2], *dinit[2] = { nullptr, nullptr }, *dout[2], *dpcm[2] = { nullptr, nullptr }, *dmags[2];
     for (int b = 0; b < 2; b++) {
+        // per-chunk magnitudes and (when the caller injects none) start signals have buffers of their own, so the
+        // next chunk's are produced on st_pre while this chunk iterates: HBM-bound work under FP32-bound work
+        if (int rc = ensure(ctx, S_PM0 + b, (size_t)cpc * n_frames * kMagStride * 4, &dmags[b])) return rc;
+        if (!init) { if (int rc = ensure(ctx, S_PI0 + b, (size_t)cpc * ola * 4, &dinit[b])) return rc; }
         if (int rc = ensure(ctx, S_CH0 + b, (size_t)cpc * mel_per * 4, &dmel[b])) return rc;
         if (int rc = ensure(ctx, S_CH2 + b, (size_t)cpc * ola * 4, &dout[b])) return rc;
         if (init) { if (int rc = ensure(ctx, S_CH4 + b, (size_t)cpc * ola * 4, &dinit[b])) return rc; }
         if (pcm16) { if (int rc = ensure(ctx, S_CH6 + b, (size_t)cpc * ola * 2, &dpcm[b])) return rc; }
     }
-    cudaEvent_t up[2], done[2], down[2];
+    cudaEvent_t up[2], done[2], down[2], pre[2];
     for (int b = 0; b < 2; b++) {
         CU(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pre[b], cudaEventDisableTiming));
     }
     int rc = 0;
     // chunk schedule: a small first chunk (short pipeline fill), full chunks, then a taper down to 16 clips
@@ -1030,10 +1040,19 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         cudaMemcpyAsync(dmel[b], mel + (size_t)c0 * mel_per, (size_t)nc * mel_per * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
         if (init) cudaMemcpyAsync(dinit[b], init + (size_t)c0 * ola, (size_t)nc * ola * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
         cudaEventRecord(up[b], ctx->st_h2d);
-        cudaStreamWaitEvent(ctx->st, up[b], 0);
+        cudaStreamWaitEvent(ctx->st_pre, up[b], 0);
+        if (c >= 2) cudaStreamWaitEvent(ctx->st_pre, done[b], 0);        // chunk c-2 no longer reads dmags[b] / dinit[b]
+        rc = mags_dev<float>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (float*)dmags[b], ctx->st_pre);
+        if (!rc && !init) {
+            k_fill_uniform<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st_pre>>>((float*)dinit[b], (long)nc * ola,
+                                                                                 seed + (unsigned long long)c0);
+            ctx->launches++;
+        }
+        cudaEventRecord(pre[b], ctx->st_pre);
+        cudaStreamWaitEvent(ctx->st, pre[b], 0);
         if (c >= 2) cudaStreamWaitEvent(ctx->st, down[b], 0);            // output buffer of chunk c-2 drained
-        rc = from_mel_dev_impl<float>(ctx, cfg, (const float*)dmel[b], nc, n_frames, (const float*)dinit[b],
-                                      seed + (unsigned long long)c0, ola, (float*)dout[b]);
+        if (!rc) rc = gl_dev(ctx, cfg, (const float*)dmags[b], nc, n_frames, (const float*)dinit[b],
+                             seed + (unsigned long long)c0, ola, (float*)dout[b]);
         if (pcm16 && !rc) {
             k_f32_to_pcm16<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st>>>((const float*)dout[b], (short*)dpcm[b], (long)nc * ola);
             ctx->launches++;
@@ -1046,8 +1065,9 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
             cudaMemcpyAsync((float*)out + (size_t)c0 * ola, dout[b], (size_t)nc * ola * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
         cudaEventRecord(down[b], ctx->st_d2h);
     }
-    cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_d2h);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); }
+    cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_pre); cudaStreamSynchronize(ctx->st);
+    cudaStreamSynchronize(ctx->st_d2h);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); cudaEventDestroy(pre[b]); }
     if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
