@@ -1014,7 +1014,7 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         CU(cudaEventCreateWithFlags(&pre[b], cudaEventDisableTiming));
     }
     int rc = 0;
-    // chunk schedule: a small first chunk (short pipeline fill), full chunks, then a taper down to 16 clips
+    // chunk schedule: a small first chunk (short pipeline fill), full chunks, then a taper down to 64 clips (GOMEL_CHUNK_TAPER_MIN)
     // (short drain: the last D2H is the only copy that cannot overlap compute)
     std::vector<int> sizes;
     {
