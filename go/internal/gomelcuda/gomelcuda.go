@@ -89,10 +89,16 @@ func melToHz(v float64) float64 { return 700.0 * (math.Exp(v/1127.0) - 1.0) } //
 // them to the library, so the two 1-ulp-fragile band edges fall where the reference puts them.
 // Registered once per key; cfg.MelFmin / cfg.MelFmax of the compute calls select the set.
 func (x *Ctx) SetMelTables(cfg Config, fmin, fmax float64) error {
+	return x.setMelTables(cfg, fmin, fmax, false)
+}
+
+// force: register again even if this Ctx believes the key is registered (the library evicts the least
+// recently used of its 64 table sets; a mel call then returns GOMEL_E_STATE and is retried once).
+func (x *Ctx) setMelTables(cfg Config, fmin, fmax float64, force bool) error {
 	key := [4]float64{float64(cfg.NFFT), float64(cfg.NMels), fmin, fmax}
 	x.mu.Lock()
 	defer x.mu.Unlock()
-	if x.registered[key] {
+	if x.registered[key] && !force {
 		return nil
 	}
 	cfg.MelFmin, cfg.MelFmax = fmin, fmax
@@ -140,21 +146,40 @@ func (x *Ctx) ToMel(cfg Config, wav []float64) ([][2]float64, error) {
 	}
 	out := make([][2]float64, frames*cfg.NMels)
 	cc := cfg.c()
-	rc := C.gomel_to_mel(x.h, &cc, (*C.double)(unsafe.Pointer(&wav[0])), C.long(len(wav)),
-		(*C.double)(unsafe.Pointer(&out[0])))
+	call := func() C.int {
+		return C.gomel_to_mel(x.h, &cc, (*C.double)(unsafe.Pointer(&wav[0])), C.long(len(wav)),
+			(*C.double)(unsafe.Pointer(&out[0])))
+	}
+	rc := call()
+	if rc == C.GOMEL_E_STATE && x.setMelTables(cfg, cfg.MelFmin, cfg.MelFmax, true) == nil {
+		rc = call()
+	}
 	return out, x.err(rc)
 }
 
 func (x *Ctx) FromMel(cfg Config, mel [][2]float64, init []float64) ([]float64, error) {
+	if cfg.NMels <= 0 || len(mel) == 0 || len(mel)%cfg.NMels != 0 {
+		// the reference strides by NumMels without a length check and panics (mel/impl.go:366-372)
+		return nil, errors.New("gomel: len(ospectrum) is not a positive multiple of NumMels")
+	}
 	frames := len(mel) / cfg.NMels
 	out := make([]float64, cfg.NFFT+(frames-1)*cfg.Hop)
+	if len(init) != 0 && len(init) != len(out) {
+		return nil, errors.New("gomel: start signal length != Resolut + (frames-1)*Window")
+	}
 	cc := cfg.c()
 	var ip *C.double
 	if len(init) > 0 {
 		ip = (*C.double)(unsafe.Pointer(&init[0]))
 	}
-	rc := C.gomel_from_mel(x.h, &cc, (*C.double)(unsafe.Pointer(&mel[0])), C.long(frames), ip, 0,
-		(*C.double)(unsafe.Pointer(&out[0])))
+	call := func() C.int {
+		return C.gomel_from_mel(x.h, &cc, (*C.double)(unsafe.Pointer(&mel[0])), C.long(frames), ip, 0,
+			(*C.double)(unsafe.Pointer(&out[0])))
+	}
+	rc := call()
+	if rc == C.GOMEL_E_STATE && x.setMelTables(cfg, cfg.MelFmin, cfg.MelFmax, true) == nil {
+		rc = call()
+	}
 	return out, x.err(rc)
 }
 
@@ -171,6 +196,9 @@ func (x *Ctx) ToPhase(cfg Config, wav []float64) ([][2]float64, error) {
 }
 
 func (x *Ctx) FromPhase(cfg Config, spec [][2]float64) ([]float64, error) {
+	if cfg.NFreqs <= 0 || len(spec) == 0 || len(spec)%cfg.NFreqs != 0 {
+		return nil, errors.New("gomel: len(ospectrum) is not a positive multiple of NumFreqs")
+	}
 	frames := len(spec) / cfg.NFreqs
 	out := make([]float64, cfg.NFFT+(frames-1)*cfg.Hop)
 	cc := cfg.c()
@@ -180,6 +208,9 @@ func (x *Ctx) FromPhase(cfg Config, spec [][2]float64) ([]float64, error) {
 }
 
 func (x *Ctx) Image(buf [][2]float64, mels int) ([]uint16, error) {
+	if mels <= 0 || len(buf) < mels {
+		return nil, errors.New("gomel: fewer entries than one column")
+	}
 	out := make([]uint16, (len(buf)/mels)*mels)
 	rc := C.gomel_image(x.h, (*C.double)(unsafe.Pointer(&buf[0])), C.long(len(buf)), C.int(mels),
 		(*C.ushort)(unsafe.Pointer(&out[0])), nil)
