@@ -1022,7 +1022,13 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         const char* ef = getenv("GOMEL_CHUNK_TAPER_MIN");           // smallest tapered chunk (tuning knob)
         int floor_ = ef ? atoi(ef) : 64;
         if (floor_ < 1) floor_ = 1;
-        const int first = cpc >= 128 ? cpc / 4 : cpc;
+        // first chunk: its H2D is the pipeline fill, so it is small -- but not so small that the second chunk's
+        // H2D outlasts its compute
+        int first = cpc >= 128 ? (cpc / 8 > 64 ? cpc / 8 : 64) : cpc;
+        if (const char* e1 = getenv("GOMEL_CHUNK_FIRST")) {        // clips in the first chunk (tuning knob)
+            const int v = atoi(e1);
+            if (v >= 1 && v <= cpc) first = v;
+        }
         auto push = [&](int n) { n = n < left ? n : left; if (n > 0) { sizes.push_back(n); left -= n; } };
         push(first);
         int taper = 0;
@@ -1044,8 +1050,10 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         if (c >= 2) cudaStreamWaitEvent(ctx->st_pre, done[b], 0);        // chunk c-2 no longer reads dmags[b] / dinit[b]
         rc = mags_dev<float>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (float*)dmags[b], ctx->st_pre);
         if (!rc && !init) {
-            k_fill_uniform<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st_pre>>>((float*)dinit[b], (long)nc * ola,
-                                                                                 seed + (unsigned long long)c0);
+            // indexed by the sample's position in the whole batch: the start signals do not depend on the chunking
+            // and equal those of gomel_from_mel_dev(seed) on the same batch
+            k_fill_uniform<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st_pre>>>((float*)dinit[b], (long)nc * ola, seed,
+                                                                                 (long)c0 * ola);
             ctx->launches++;
         }
         cudaEventRecord(pre[b], ctx->st_pre);

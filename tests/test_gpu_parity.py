@@ -303,6 +303,30 @@ def test_batch_from_mel_pcm16_is_the_wav_quantisation_of_the_float_output(mctx, 
     assert np.abs(f32[0]).max() > 1.0 and np.array_equal(pcm, want)
 
 
+def test_batch_start_signals_do_not_depend_on_the_chunking(mctx, lib):
+    """init = NULL: the device draws U[0,1) per sample from (seed, position in the batch) -- any chunk size and the
+    device-resident call give the same waveforms"""
+    cfg = mel_cfg(lib, iters=2)
+    n_clips, frames = 7, 6
+    ola = 4096 + (frames - 1) * 1280
+    mel32 = np.random.default_rng(5).uniform(-9.0, 2.0, (n_clips, frames * 192, 2)).astype(np.float32)
+    outs = []
+    for chunk in (2, 3, 7):
+        out = np.empty((n_clips, ola), np.float32)
+        mctx.check(mctx.lib.gomel_from_mel_batch_host(mctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), n_clips, frames,
+                                                      None, 1234, out.ctypes.data_as(C.c_void_p), chunk))
+        outs.append(out)
+    d_mel, d_out = mctx.dev_malloc(mel32.nbytes), mctx.dev_malloc(n_clips * ola * 4)
+    mctx.h2d(d_mel, mel32)
+    mctx.check(mctx.lib.gomel_from_mel_dev(mctx.h, C.byref(cfg), d_mel, n_clips, frames, None, 1234, ola, d_out))
+    dev = np.empty((n_clips, ola), np.float32)
+    mctx.d2h(dev, d_out)
+    mctx.dev_free(d_mel)
+    mctx.dev_free(d_out)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], dev)
+    assert np.abs(dev).max() > 0
+
+
 def test_batch_to_mel_matches_oracle(mctx, lib, oracle):
     cfg = mel_cfg(lib)
     n_clips, n = 7, 30000

@@ -34,14 +34,16 @@ def run(chunk):
                                                 None, 1, h_out.ctypes.data_as(C.c_void_p), chunk))
 
 
-for chunk in (256, 384, 512, 768, 1024):
-    for floor_ in (32, 64, 128, 256):
-        if floor_ > chunk // 2:
-            continue
-        os.environ["GOMEL_CHUNK_TAPER_MIN"] = str(floor_)
-        run(chunk); run(chunk)
-        t0 = time.perf_counter()
-        for _ in range(4):
-            run(chunk)
-        ms = (time.perf_counter() - t0) * 1e3 / 4
-        print(f"chunk {chunk:5d} taper_min {floor_:4d}: {ms:7.2f} ms  {audio / ms:7.1f} k audio-s/s", flush=True)
+combos = [(c, f, 0) for c in (256, 384, 512, 768, 1024) for f in (32, 64, 128, 256) if f <= c // 2]
+if len(sys.argv) > 1 and sys.argv[1] == "first":                 # sweep the first chunk instead
+    combos = [(512, 64, f1) for f1 in (32, 64, 96, 128, 192, 256)] + [(384, 64, 64), (640, 64, 128)]
+for chunk, floor_, first in combos:
+    os.environ["GOMEL_CHUNK_TAPER_MIN"] = str(floor_)
+    if first:
+        os.environ["GOMEL_CHUNK_FIRST"] = str(first)
+    run(chunk); run(chunk)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        run(chunk)
+    ms = (time.perf_counter() - t0) * 1e3 / 5
+    print(f"chunk {chunk:5d} taper_min {floor_:4d} first {first:4d}: {ms:7.2f} ms  {audio / ms:7.1f} k audio-s/s", flush=True)
