@@ -145,29 +145,31 @@ def _read_png16(path):
     bpp = ch * 2
     raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + w * bpp)
     out = np.zeros((h, w * bpp), np.uint8)
-    prev = np.zeros(w * bpp, np.int32)
+    prev = np.zeros((w, bpp), np.int32)
     for y in range(h):
-        ft, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
-        cur = np.zeros(w * bpp, np.int32)
+        ft, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32).reshape(w, bpp)
         if ft == 0:
             cur = line
-        elif ft == 2:
+        elif ft == 2:                                   # Up
             cur = (line + prev) & 255
-        else:
-            for i in range(w * bpp):
-                a = cur[i - bpp] if i >= bpp else 0
-                b = prev[i]
-                c = prev[i - bpp] if i >= bpp else 0
-                if ft == 1:
-                    pr = a
-                elif ft == 3:
+        elif ft == 1:                                   # Sub: running sum per byte lane
+            cur = np.cumsum(line, axis=0) & 255
+        else:                                           # Average / Paeth: sequential in x, all byte lanes at once
+            cur = np.zeros((w, bpp), np.int32)
+            a = np.zeros(bpp, np.int32)
+            c = np.zeros(bpp, np.int32)
+            for x in range(w):
+                b = prev[x]
+                if ft == 3:
                     pr = (a + b) >> 1
                 else:
                     p = a + b - c
-                    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
-                    pr = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
-                cur[i] = (line[i] + pr) & 255
-        out[y] = cur
+                    pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+                    pr = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+                a = (line[x] + pr) & 255
+                cur[x] = a
+                c = b
+        out[y] = cur.reshape(-1)
         prev = cur
     px = out.view(">u2").astype(np.uint16).reshape(h, w, ch)
     if ch == 1:
