@@ -222,3 +222,24 @@ def test_volume_boost_doubles_peak(oracle):
     assert abs(np.abs(b).max() / np.abs(a).max() - 2.0) < 1e-12
     c = oracle.from_phase(oracle.config(num_freqs=768, volume_boost=0.0), spec)     # 0 = no boost (phase/phase.go:146)
     assert np.array_equal(a, c)
+
+
+def test_oracle_is_clean_under_asan_ubsan(tmp_path):
+    """the checker itself is checked -- every oracle entry point on small inputs (both
+    geometries, edge lengths) in a build with AddressSanitizer + UndefinedBehaviorSanitizer"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "orc_san")
+    cmd = ["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined",
+           "-o", exe, os.path.join(root, "tests", "c", "oracle_sanitize.c"), os.path.join(root, "oracle", "gomel_oracle.c"), "-lm"]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip("toolchain without sanitizer runtime")
+    assert b.returncode == 0, b.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", LD_PRELOAD=""))
+    assert r.returncode == 0 and "oracle sanitize ok" in r.stdout, r.stdout + r.stderr
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr
