@@ -122,3 +122,57 @@ def test_time_split_partition(frames, world, tile):
         assert a == pos and a % T == 0 and n > 0
         pos += n
     assert pos == frames
+
+
+# ---- properties of the oracle itself (the mel path has no reference golden vectors: DESIGN.md section 2) ----------
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 2**31), gain=st.floats(0.25, 8.0), geo=st.sampled_from([(4096, 1280, 192, 16000.0), (2048, 256, 160, 8000.0)]))
+def test_oracle_to_mel_is_homogeneous_and_shift_covariant(oracle, seed, gain, geo):
+    """|X| is linear in the signal and domel is a linear band average, so above the 1e-5 floor
+    exp(ToMel(g*x)) = g * exp(ToMel(x)); and delaying x by one hop moves every frame by one column"""
+    n_fft, hop, mels, fmax = geo
+    cfg = oracle.config(num_mels=mels, window=hop, resolut=n_fft, mel_fmax=fmax)
+    x = np.random.default_rng(seed).standard_normal(20 * hop) * 0.3
+    a = np.exp(oracle.to_mel(cfg, x))
+    b = np.exp(oracle.to_mel(cfg, gain * x))
+    ok = (a > 2e-5) & (b > 2e-5)
+    assert ok.mean() > 0.9 and np.allclose(b[ok], gain * a[ok], rtol=1e-12)
+    assert a.min() >= 1e-5 * (1 - 1e-15)                                  # spectral_normalize floor
+    xs = np.concatenate([np.zeros(hop), x])                               # one hop later
+    c = np.exp(oracle.to_mel(cfg, xs)).reshape(-1, mels, 2)
+    a3 = a.reshape(-1, mels, 2)
+    k = (len(x) - n_fft) // hop + 1                                       # frames made of signal samples only
+    assert np.allclose(c[1:k + 1], a3[:k], rtol=1e-12, atol=1e-15)
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 2**31), frames=st.integers(1, 6))
+def test_oracle_griffin_lim_structure(oracle, seed, frames):
+    """mel.ISTFT (mel/mel.go:76-139): zero iterations return the start signal; the result does not depend on the
+    start signal's scale (only its phases are kept)"""
+    rng = np.random.default_rng(seed)
+    mel = rng.uniform(-6.0, 1.0, (frames * 192, 2))
+    init = rng.random(4096 + (frames - 1) * 1280) + 0.05
+    assert np.array_equal(oracle.from_mel(oracle.config(gl_iters=0), mel, init), init)
+    one = oracle.from_mel(oracle.config(gl_iters=1), mel, init)
+    scaled = oracle.from_mel(oracle.config(gl_iters=1), mel, 3.0 * init)
+    assert np.allclose(one, scaled, rtol=1e-9, atol=1e-12)
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 2**31), nf=st.sampled_from([384, 768, 836, 2048]), boost=st.sampled_from([0.0, 0.5, 2.0]))
+def test_oracle_phase_roundtrip_recovers_the_interior(oracle, seed, nf, boost):
+    """FromPhase(ToPhase(x)) (phase/phase.go:41-153): with all 2048 bins kept and the DC bin (dropped by the
+    format) absent from x, the interior (window-sum above the 0.5*max threshold) is x itself, times VolumeBoost"""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(30000) * 0.2
+    x -= x.mean()
+    cfg = oracle.config(num_freqs=nf, volume_boost=boost)
+    spec = oracle.to_phase(cfg, x)
+    y = oracle.from_phase(cfg, spec)
+    assert len(spec) % nf == 0 and len(y) == 4096 + (len(spec) // nf - 1) * 1280
+    if nf == 2048:
+        g = boost if boost != 0 else 1.0
+        sl = slice(4096, 26000)
+        # per-frame DC (mean of the windowed frame) is dropped with bin 0: small, not zero
+        assert np.abs(y[sl] - g * x[sl]).max() < 0.05 * g
