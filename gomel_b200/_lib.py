@@ -42,6 +42,7 @@ SIGNATURES = {
     "gomel_version": (C.c_char_p, []),
     "gomel_launch_count": (C.c_ulonglong, [_vp]),
     "gomel_set_tile_frames": (C.c_int, [_vp, C.c_int]),
+    "gomel_set_lead_f64": (C.c_int, [_vp, C.c_int]),
     "gomel_frames": (C.c_int, [_cp, C.c_long, _lp, _lp, _lp]),
     "gomel_ola_len": (C.c_long, [_cp, C.c_long]),
     "gomel_set_mel_tables": (C.c_int, [_vp, _cp, _ip, _ip, _dp, _ip, _ip, _dp]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "gomel_timer_start": (C.c_int, [_vp]),
     "gomel_timer_stop": (C.c_int, [_vp, _fp]),
     "gomel_last_hot_kernel_ms": (C.c_int, [_vp, _fp, _ip]),
+    "gomel_last_lead_kernel_ms": (C.c_int, [_vp, _fp, _ip]),
     "gomel_to_mel_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, C.c_long, C.c_long, _vp]),
     "gomel_to_phase_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, C.c_long, C.c_long, _vp]),
     "gomel_stft_dev": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, C.c_long, C.c_long, _vp]),
@@ -110,7 +112,8 @@ def load():
     return _lib
 
 
-FLAG_F64 = 1          # strict float64 Griffin-Lim (include/gomel_cuda.h GOMEL_FLAG_F64)
+FLAG_F64 = 1          # every Griffin-Lim iteration in float64 on the fused kernel (GOMEL_FLAG_F64)
+FLAG_F64_REF = 2      # round-1 strict float64 path, test instrument (GOMEL_FLAG_F64_REF)
 
 
 def make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=2, tune_mul=1.0, tune_add=0.0,
@@ -244,6 +247,13 @@ class Context:
     def set_tile_frames(self, t):
         self.check(self.lib.gomel_set_tile_frames(self.h, int(t)))
 
+    def set_lead_f64(self, k):
+        """float64 lead iterations of Griffin-Lim (default 4); returns the previous value"""
+        rc = self.lib.gomel_set_lead_f64(self.h, int(k))
+        if rc < 0:
+            self.check(rc)
+        return rc
+
     # ---- host-buffer API -------------------------------------------------------------
     def to_mel(self, cfg, wav):
         wav = np.ascontiguousarray(wav, np.float64)
@@ -368,6 +378,15 @@ def _hot(self):
 
 
 Context.last_hot_kernel_ms = _hot
+
+
+def _lead(self):
+    ms, n = C.c_float(), C.c_int()
+    self.check(self.lib.gomel_last_lead_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
+Context.last_lead_kernel_ms = _lead
 
 _default = {}
 

@@ -4,6 +4,7 @@
 #include "../../include/gomel_cuda.h"
 #include "kernels.cuh"
 #include "kernels_f64.cuh"
+#include "gl_f64.cuh"
 
 #include <cmath>
 #include <dlfcn.h>
@@ -50,7 +51,12 @@ constexpr size_t kMaxMelTables = 64;
 static_assert(sizeof(gomel_config) == 72, "gomel_config layout is part of the ABI (ctypes / cgo mirror it)");
 
 enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
-               S_MISC, S_CH0, S_CH1, S_CH2, S_CH3, S_CH4, S_CH5, S_CH6, S_CH7, S_PM0, S_PM1, S_PI0, S_PI1, S_COUNT };
+               S_MISC, S_LSIGA, S_LSIGB, S_LHB0, S_LHB1, S_LMAGS, S_PIPE, S_COUNT = S_PIPE + 3 * 8 };
+// chunk buffers of the pipelined host batches: kPipeSets sets of (mel | signal in, out, init, pcm, mags32, mags64)
+constexpr int kPipeSets = 3;
+enum PipeKind { P_IN = 0, P_OUT, P_INIT, P_PCM, P_MAGS32, P_MAGS64 };
+constexpr int pipe_slot(int set, int kind) { return S_PIPE + set * 8 + kind; }
+constexpr int kDefaultLeadF64 = 4;           // Griffin-Lim iterations run in float64 before the float32 ones
 
 }  // namespace
 
@@ -64,8 +70,11 @@ struct gomel_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
     cudaStream_t st_pre = nullptr;    // batch pipeline: magnitudes / start signal of the next chunk, beside the iterations
     int gl_streams = 2;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
     int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
+    int lead_launches = 0;    // float64 lead iterations of the last Griffin-Lim, bracketed by ev_l0/ev_l1
+    int lead_f64 = kDefaultLeadF64;   // gomel_set_lead_f64 / GOMEL_LEAD_F64
+    double* d_tables_d64 = nullptr;   // gl_f64.cuh tables (built on first use)
     float4* d_tables = nullptr;
     float4* d_tables_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     double* d_tables64 = nullptr;     // strict float64 path (built on first use)
@@ -307,83 +316,231 @@ int fwd_dev(gomel_ctx* ctx, const gomel_config* cfg, int mode, const float* d_si
     return 0;
 }
 
-int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_mags, int n_clips, long n_frames,
-           const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
+// ---- float64 tables of gl_f64.cuh (root powers 1,2,4,8 for both twiddle stages, half Hann window), built once
+int ensure_tables_d64(gomel_ctx* ctx)
+{
+    namespace D = gomel::d64;
+    if (ctx->d_tables_d64) return 0;
+    std::vector<double> blob(D::kTableBytes / 8, 0.0);
+    double* T1 = blob.data();
+    double* T2 = T1 + D::kT1Cells * 2;
+    double* win = T2 + D::kT2Cells * 2;
+    const double two_pi = 6.283185307179586476925286766559;
+    const int pw[4] = { 1, 2, 4, 8 };
+    for (int i = 0; i < 4; i++) {
+        for (int t = 0; t < 256; t++) {
+            const double a = two_pi * (double)((t * pw[i]) % 4096) / 4096.0;
+            T1[(i * 256 + t) * 2] = std::cos(a); T1[(i * 256 + t) * 2 + 1] = -std::sin(a);
+        }
+        for (int n0 = 0; n0 < 16; n0++) {
+            const double a = two_pi * (double)((n0 * pw[i]) % 256) / 256.0;
+            T2[(i * 16 + n0) * 2] = std::cos(a); T2[(i * 16 + n0) * 2 + 1] = -std::sin(a);
+        }
+    }
+    for (int n = 0; n < kN / 2; n++) win[n] = 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1)));
+    CU(cudaMalloc(&ctx->d_tables_d64, D::kTableBytes));
+    CU(cudaMemcpy(ctx->d_tables_d64, blob.data(), D::kTableBytes, cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(D::k_gl_iter_f64<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes));
+    return 0;
+}
+
+// How many of `iters` Griffin-Lim iterations run in float64 (gl_f64.cuh) before the float32 kernel takes over.
+// GOMEL_FLAG_F64: all of them.  The Resolut 2048 geometry has no float64 kernel.
+int lead_iters(const gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo)
+{
+    if (geo.alt) return 0;
+    const int iters = cfg->gl_iters < 0 ? 0 : cfg->gl_iters;
+    if (cfg->flags & GOMEL_FLAG_F64) return iters;
+    return ctx->lead_f64 < iters ? ctx->lead_f64 : iters;
+}
+
+// Buffers of one Griffin-Lim run.  Exactly one of out32 / out64 is set (out64 only when every iteration is
+// float64); at most one of init32 / init64 (neither: U[0,1) from the seed).
+struct GlIO {
+    const float* mags32 = nullptr; const double* mags64 = nullptr;
+    const float* init32 = nullptr; const double* init64 = nullptr;
+    float* out32 = nullptr; double* out64 = nullptr;
+};
+
+// grow-only scratch of gl_dev for a batch of this size; called up front by the chunked pipelines so that no
+// (device-synchronising) reallocation happens between chunks
+int gl_reserve(gomel_ctx* ctx, const gomel_config* cfg, int n_clips, long n_frames, long sig_stride, bool need_init)
+{
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
+    const int iters = cfg->gl_iters, lead = lead_iters(ctx, cfg, geo);
+    const long ola = geo.ola(n_frames);
+    void* b;
+    const size_t sig_bytes = (size_t)n_clips * sig_stride * 4;
+    const Tiling tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves);
+    const size_t hb_elems = (size_t)n_clips * (tl.n_tiles + 1) * geo.halo + 4;
+    if (need_init) { if (int rc = ensure(ctx, S_INIT, sig_bytes, &b)) return rc; }
+    if (iters - lead > 0) {
+        if (iters - lead > 1 || lead > 0) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &b)) return rc; }
+        if (int rc = ensure(ctx, S_HB0, hb_elems * 4, &b)) return rc;
+        if (int rc = ensure(ctx, S_HB1, hb_elems * 4, &b)) return rc;
+    }
+    if (lead > 0) {
+        if (int rc = ensure(ctx, S_LSIGA, sig_bytes * 2, &b)) return rc;
+        if (int rc = ensure(ctx, S_LSIGB, sig_bytes * 2, &b)) return rc;
+        if (int rc = ensure(ctx, S_LHB0, hb_elems * 8, &b)) return rc;
+        if (int rc = ensure(ctx, S_LHB1, hb_elems * 8, &b)) return rc;
+        if (int rc = ensure_tables_d64(ctx)) return rc;
+    }
+    return 0;
+}
+
+int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips, long n_frames,
+           unsigned long long seed, long sig_stride)
 {
     Geo geo;
     if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     const long ola = geo.ola(n_frames);
     if (sig_stride < ola) return fail(ctx, GOMEL_E_ARG, "sig_stride < ola_len");
-    if (d_init == d_out) return fail(ctx, GOMEL_E_ARG, "d_init and d_out must not alias");
+    if (io.init32 && io.init32 == io.out32) return fail(ctx, GOMEL_E_ARG, "d_init and d_out must not alias");
     const int iters = cfg->gl_iters;
     if (iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
-    const size_t sig_bytes = (size_t)n_clips * sig_stride * 4;
-    if (!d_init) {
-        void* b; if (int rc = ensure(ctx, S_INIT, sig_bytes, &b)) return rc;
-        k_fill_uniform<<<grid_1d((long)n_clips * sig_stride, 256), 256, 0, ctx->st>>>((float*)b, (long)n_clips * sig_stride, seed);
+    const int lead = lead_iters(ctx, cfg, geo);
+    if (io.out64 && lead != iters) return fail(ctx, GOMEL_E_ARG, "float64 output needs GOMEL_FLAG_F64");
+    if ((lead > 0 && !io.mags64) || (iters - lead > 0 && !io.mags32)) return fail(ctx, GOMEL_E_ARG, "magnitudes missing");
+    const long n_sig = (long)n_clips * sig_stride;
+    const size_t sig_bytes = (size_t)n_sig * 4;
+    const bool fill = !io.init32 && !io.init64;
+    if (int rc = gl_reserve(ctx, cfg, n_clips, n_frames, sig_stride, fill)) return rc;
+    const float* init32 = io.init32;
+    if (fill) {
+        float* b = (float*)ctx->scratch[S_INIT];
+        k_fill_uniform<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(b, n_sig, seed);
         ctx->launches++;
-        d_init = (const float*)b;
+        init32 = b;
     }
+    ctx->hot_launches = 0; ctx->lead_launches = 0;
     if (iters == 0) {       // mel/mel.go:85: zero iterations return the start signal
-        CU(cudaMemcpyAsync(d_out, d_init, sig_bytes, cudaMemcpyDeviceToDevice, ctx->st));
+        if (io.out64) {
+            if (io.init64) CU(cudaMemcpyAsync(io.out64, io.init64, (size_t)n_sig * 8, cudaMemcpyDeviceToDevice, ctx->st));
+            else { k_f32_to_f64<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(init32, io.out64, n_sig, 1.0); ctx->launches++; }
+        } else if (io.init64) { d64::k_f64_to_f32<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(io.init64, io.out32, n_sig); ctx->launches++; }
+        else CU(cudaMemcpyAsync(io.out32, init32, sig_bytes, cudaMemcpyDeviceToDevice, ctx->st));
         return 0;
     }
-    SynParams p = {};
-    p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
-    p.tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves);
-    p.mags = d_mags;
-    void *tmp = nullptr, *hb[2] = { nullptr, nullptr };
-    if (iters > 1) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &tmp)) return rc; }
-    p.hb_tiles = p.tl.n_tiles + 1; p.tile_lo = 0; p.tiles_in_launch = p.tl.n_tiles;
-    const size_t hb_bytes = (size_t)n_clips * p.hb_tiles * geo.halo * 4 + 16;
-    if (int rc = ensure(ctx, S_HB0, hb_bytes, &hb[0])) return rc;
-    if (int rc = ensure(ctx, S_HB1, hb_bytes, &hb[1])) return rc;
-    const long grid = (long)n_clips * p.tl.n_tiles;
+    const Tiling tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves);
+    const int hb_tiles = tl.n_tiles + 1;
+    const long grid = (long)n_clips * tl.n_tiles;
     if (grid > 0x7fffffffL) return fail(ctx, GOMEL_E_ARG, "too many tiles");
-    const float* cur = d_init;
-    CU(cudaEventRecord(ctx->ev_k0, ctx->st));
     // groups of clips on concurrent streams (group g: clips [g*n/ns, (g+1)*n/ns)); every group needs whole waves
     int ns = ctx->gl_streams;
     while (ns > 1 && grid / ns < (long)kGlCtasPerSm * ctx->sm_count) ns--;
     if (ns > n_clips) ns = n_clips;
     cudaStream_t gs[4] = { ctx->st, ctx->st_gl[0], ctx->st_gl[1], ctx->st_gl[2] };
-    if (ns > 1) {
-        CU(cudaEventRecord(ctx->ev_fork, ctx->st));
-        for (int g = 1; g < ns; g++) CU(cudaStreamWaitEvent(gs[g], ctx->ev_fork, 0));
-    }
-    for (int i = 0; i < iters; i++) {
-        float* dst = (((iters - 1 - i) & 1) == 0) ? d_out : (float*)tmp;
-        p.sig_in = cur; p.sig_out = dst;
-        p.hb_in = (i == 0) ? nullptr : (const float*)hb[(i - 1) & 1];
-        p.hb_out = (float*)hb[i & 1];
+    auto c_lo = [&](int g) { return (int)((long)n_clips * g / ns); };
+    auto fork = [&]() -> int {
+        if (ns > 1) {
+            CU(cudaEventRecord(ctx->ev_fork, ctx->st));
+            for (int g = 1; g < ns; g++) CU(cudaStreamWaitEvent(gs[g], ctx->ev_fork, 0));
+        }
+        return 0;
+    };
+    auto join = [&]() -> int {
+        for (int g = 1; g < ns; g++) {
+            CU(cudaEventRecord(ctx->ev_join[g - 1], gs[g]));
+            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_join[g - 1], 0));
+        }
+        return 0;
+    };
+
+    float* tmp = (float*)ctx->scratch[S_SIGTMP];
+    const float* cur32 = init32;
+    // ---------------- float64 lead iterations
+    if (lead > 0) {
+        double* sg[2] = { (double*)ctx->scratch[S_LSIGA], (double*)ctx->scratch[S_LSIGB] };
+        double* hb[2] = { (double*)ctx->scratch[S_LHB0], (double*)ctx->scratch[S_LHB1] };
+        const double* cur = io.init64;
+        int w = 0;                                  // next buffer to write
+        if (!cur) {
+            k_f32_to_f64<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(init32, sg[0], n_sig, 1.0);
+            ctx->launches++;
+            cur = sg[0]; w = 1;
+        }
+        CU(cudaEventRecord(ctx->ev_l0, ctx->st));
+        if (int rc = fork()) return rc;
+        d64::GLParams p = {};
+        p.tables = ctx->d_tables_d64; p.tl = tl; p.mags = io.mags64;
+        p.hb_tiles = hb_tiles; p.tile_lo = 0; p.tiles_in_launch = tl.n_tiles;
+        for (int i = 0; i < lead; i++) {
+            p.sig_in = cur; p.sig_out = sg[w];
+            p.hb_in = (i == 0) ? nullptr : hb[(i - 1) & 1];
+            p.hb_out = hb[i & 1];
+            for (int g = 0; g < ns; g++) {
+                p.clip0 = c_lo(g);
+                const unsigned gg = (unsigned)((long)(c_lo(g + 1) - c_lo(g)) * tl.n_tiles);
+                d64::k_gl_iter_f64<kHS><<<gg, kThreads, d64::kSmemBytes, gs[g]>>>(p);
+                ctx->launches++;
+            }
+            cur = sg[w]; w ^= 1;
+        }
+        double* fin = const_cast<double*>(cur);     // one of sg[]: lead >= 1
+        // hand-over: fold the head partials in, then narrow to float32 (or deliver float64) -- per group, on its stream
+        float* conv = nullptr;
+        if (iters > lead) conv = ((((iters - 1 - lead) & 1) == 0) ? tmp : io.out32);     // not the first float32 iteration's output
+        else if (io.out32) conv = io.out32;
         for (int g = 0; g < ns; g++) {
-            const int c0 = (int)((long)n_clips * g / ns), c1 = (int)((long)n_clips * (g + 1) / ns);
-            p.clip0 = c0;
-            const unsigned gg = (unsigned)((long)(c1 - c0) * p.tl.n_tiles);
+            const long c0 = c_lo(g), nc = c_lo(g + 1) - c0;
+            if (tl.n_tiles > 1) {
+                d64::k_halo_fix_f64<<<(unsigned)(nc * (tl.n_tiles - 1)), 256, 0, gs[g]>>>(
+                    fin + c0 * sig_stride, hb[(lead - 1) & 1] + c0 * hb_tiles * geo.halo, tl, geo.hop, geo.halo, 1, hb_tiles);
+                ctx->launches++;
+            }
+            if (conv) {
+                d64::k_f64_to_f32<<<grid_1d(nc * sig_stride, 256), 256, 0, gs[g]>>>(fin + c0 * sig_stride, conv + c0 * sig_stride, nc * sig_stride);
+                ctx->launches++;
+            } else {
+                CU(cudaMemcpyAsync(io.out64 + c0 * sig_stride, fin + c0 * sig_stride, (size_t)nc * sig_stride * 8, cudaMemcpyDeviceToDevice, gs[g]));
+            }
+        }
+        if (int rc = join()) return rc;
+        CU(cudaEventRecord(ctx->ev_l1, ctx->st));
+        ctx->lead_launches = lead;
+        cur32 = conv;
+        if (iters == lead) { CU(cudaGetLastError()); return 0; }
+    }
+    // ---------------- float32 iterations
+    SynParams p = {};
+    p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
+    p.tl = tl;
+    p.mags = io.mags32;
+    p.hb_tiles = hb_tiles; p.tile_lo = 0; p.tiles_in_launch = tl.n_tiles;
+    float* hb[2] = { (float*)ctx->scratch[S_HB0], (float*)ctx->scratch[S_HB1] };
+    CU(cudaEventRecord(ctx->ev_k0, ctx->st));
+    if (int rc = fork()) return rc;
+    for (int i = lead; i < iters; i++) {
+        float* dst = (((iters - 1 - i) & 1) == 0) ? io.out32 : tmp;
+        p.sig_in = cur32; p.sig_out = dst;
+        p.hb_in = (i == lead) ? nullptr : (const float*)hb[(i - 1) & 1];
+        p.hb_out = hb[i & 1];
+        for (int g = 0; g < ns; g++) {
+            p.clip0 = c_lo(g);
+            const unsigned gg = (unsigned)((long)(c_lo(g + 1) - c_lo(g)) * tl.n_tiles);
             if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
             else k_gl_iter<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
             ctx->launches++;
         }
-        cur = dst;
+        cur32 = dst;
     }
     p.clip0 = 0;
-    for (int g = 1; g < ns; g++) {
-        CU(cudaEventRecord(ctx->ev_join[g - 1], gs[g]));
-        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_join[g - 1], 0));
-    }
+    if (int rc = join()) return rc;
     CU(cudaEventRecord(ctx->ev_k1, ctx->st));
-    ctx->hot_launches = iters;          // one "launch" = one iteration over the whole batch, whatever the grouping
-    if (p.tl.n_tiles > 1) {
-        k_halo_fix<<<(unsigned)(grid - n_clips), 256, 0, ctx->st>>>(d_out, (const float*)hb[(iters - 1) & 1], p.tl, geo.hop,
-                                                                  geo.halo, 0, 1, p.hb_tiles, p);
+    ctx->hot_launches = iters - lead;   // one "launch" = one iteration over the whole batch, whatever the grouping
+    if (tl.n_tiles > 1) {
+        k_halo_fix<<<(unsigned)(grid - n_clips), 256, 0, ctx->st>>>(io.out32, (const float*)hb[(iters - 1) & 1], tl, geo.hop,
+                                                                  geo.halo, 0, 1, hb_tiles, p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
     return 0;
 }
 
-template <typename T>
-int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, float* d_mags, cudaStream_t stream = nullptr)
+template <typename T, typename OUT>
+int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, OUT* d_mags, cudaStream_t stream = nullptr)
 {
     if (!stream) stream = ctx->st;
     const MelTables* mt = find_mel_tables(ctx, cfg);
@@ -393,27 +550,47 @@ int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_row
     if (g > 148L * 8) g = 148L * 8;
     const size_t sm = (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double);
     if (cfg->n_fft == 256 * kAltFS)
-        k_mags_from_mel<T, kAltFS><<<(unsigned)g, 256, sm, stream>>>(
+        k_mags_from_mel<T, kAltFS, OUT><<<(unsigned)g, 256, sm, stream>>>(
             d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     else
-        k_mags_from_mel<T><<<(unsigned)g, 256, sm, stream>>>(
+        k_mags_from_mel<T, 16, OUT><<<(unsigned)g, 256, sm, stream>>>(
             d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
     ctx->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
+// both precisions of the target magnitudes a Griffin-Lim run of this config needs
 template <typename T>
-int from_mel_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, int n_clips, long n_frames,
-                      const float* d_init, unsigned long long seed, long sig_stride, float* d_out)
+int mags_for_gl(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, int slot32, int slot64, GlIO* io,
+                cudaStream_t stream = nullptr)
 {
     Geo geo;
     if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
-    if (!d_mel || !d_out || n_clips <= 0 || n_frames <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument to from_mel");
-    void* mags;
-    if (int rc = ensure(ctx, S_MAGS, (size_t)n_clips * n_frames * kMagStride * 4, &mags)) return rc;
-    if (int rc = mags_dev<T>(ctx, cfg, d_mel, (long)n_clips * n_frames, (float*)mags)) return rc;
-    return gl_dev(ctx, cfg, (const float*)mags, n_clips, n_frames, d_init, seed, sig_stride, d_out);
+    const int lead = lead_iters(ctx, cfg, geo);
+    void* m;
+    if (cfg->gl_iters - lead > 0) {
+        if (int rc = ensure(ctx, slot32, (size_t)n_rows * kMagStride * 4, &m)) return rc;
+        if (int rc = mags_dev<T, float>(ctx, cfg, d_mel, n_rows, (float*)m, stream)) return rc;
+        io->mags32 = (const float*)m;
+    }
+    if (lead > 0) {
+        if (int rc = ensure(ctx, slot64, (size_t)n_rows * kMagStride * 8, &m)) return rc;
+        if (int rc = mags_dev<T, double>(ctx, cfg, d_mel, n_rows, (double*)m, stream)) return rc;
+        io->mags64 = (const double*)m;
+    }
+    return 0;
+}
+
+template <typename T>
+int from_mel_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, int n_clips, long n_frames,
+                      GlIO io, unsigned long long seed, long sig_stride)
+{
+    Geo geo;
+    if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
+    if (!d_mel || (!io.out32 && !io.out64) || n_clips <= 0 || n_frames <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument to from_mel");
+    if (int rc = mags_for_gl<T>(ctx, cfg, d_mel, (long)n_clips * n_frames, S_MAGS, S_LMAGS, &io)) return rc;
+    return gl_dev(ctx, cfg, io, n_clips, n_frames, seed, sig_stride);
 }
 
 int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_spec, int n_clips, long n_frames,
@@ -561,6 +738,12 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         CU(cudaEventCreate(&ctx->ev1));
         CU(cudaEventCreate(&ctx->ev_k0));
         CU(cudaEventCreate(&ctx->ev_k1));
+        CU(cudaEventCreate(&ctx->ev_l0));
+        CU(cudaEventCreate(&ctx->ev_l1));
+        if (const char* e = getenv("GOMEL_LEAD_F64")) {             // float64 lead iterations, >= 0
+            const int v = atoi(e);
+            if (v >= 0) ctx->lead_f64 = v;
+        }
         std::vector<float> blob;
         build_fft_tables(blob);
         CU(cudaMalloc(&ctx->d_tables, kTableBytes));
@@ -592,6 +775,8 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_tables_alt);
     cudaFree(ctx->d_tables64);
+    cudaFree(ctx->d_tables_d64);
+    cudaEventDestroy(ctx->ev_l0); cudaEventDestroy(ctx->ev_l1);
     for (MelTables& t : ctx->mel_tabs) t.release();
     cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
@@ -610,6 +795,15 @@ int gomel_set_tile_frames(gomel_ctx* ctx, int tile_frames)
     if (!ctx || tile_frames < 0) return GOMEL_E_ARG;
     ctx->tile_override = tile_frames;
     return 0;
+}
+
+int gomel_set_lead_f64(gomel_ctx* ctx, int lead)
+{
+    if (!ctx || lead < 0) return GOMEL_E_ARG;
+    Guard g(ctx);
+    const int prev = ctx->lead_f64;
+    ctx->lead_f64 = lead;
+    return prev;
 }
 
 int gomel_frames(const gomel_config* cfg, long n_samples, long* n_padded, long* n_frames, long* ola_len)
@@ -731,8 +925,11 @@ int gomel_from_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* mel, l
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
     Geo geo;
-    if (int rc = check_cfg(ctx, cfg, (cfg && (cfg->flags & GOMEL_FLAG_F64)) ? nullptr : &geo)) return rc;
+    const bool ref64 = cfg && (cfg->flags & GOMEL_FLAG_F64_REF);
+    if (int rc = check_cfg(ctx, cfg, ref64 ? nullptr : &geo)) return rc;
     if (!mel || !wav_out || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    if (cfg->gl_iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
+    if (geo.alt && (cfg->flags & GOMEL_FLAG_F64)) return fail(ctx, GOMEL_E_UNSUPPORTED, "GOMEL_FLAG_F64 needs Resolut=4096, Window=1280");
     const long ola = geo.ola(n_frames);
     const long n_mel = n_frames * 2L * cfg->n_mels;
     void *dmel, *dinit64 = nullptr, *dinit = nullptr, *dout, *dout64;
@@ -740,21 +937,27 @@ int gomel_from_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* mel, l
     if (int rc = ensure(ctx, S_F32B, (size_t)ola * 4, &dout)) return rc;
     if (int rc = ensure(ctx, S_F64OUT, (size_t)ola * 8, &dout64)) return rc;
     CU(cudaMemcpyAsync(dmel, mel, (size_t)n_mel * 8, cudaMemcpyHostToDevice, ctx->st));
-    if (cfg->flags & GOMEL_FLAG_F64) {
-        if (cfg->gl_iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
-        return from_mel_f64(ctx, cfg, (const double*)dmel, n_frames, init_signal, seed, wav_out);
-    }
+    if (ref64) return from_mel_f64(ctx, cfg, (const double*)dmel, n_frames, init_signal, seed, wav_out);
+    const int lead = lead_iters(ctx, cfg, geo);
+    GlIO io;
     if (init_signal) {
         if (int rc = ensure(ctx, S_F64IN2, (size_t)ola * 8, &dinit64)) return rc;
-        if (int rc = ensure(ctx, S_F32A, (size_t)ola * 4, &dinit)) return rc;
         CU(cudaMemcpyAsync(dinit64, init_signal, (size_t)ola * 8, cudaMemcpyHostToDevice, ctx->st));
-        k_f64_to_f32_pad<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const double*)dinit64, ola, (float*)dinit, ola);
+        if (lead > 0 || cfg->gl_iters == 0) io.init64 = (const double*)dinit64;     // the float64 iterations start from the caller's exact signal
+        else {
+            if (int rc = ensure(ctx, S_F32A, (size_t)ola * 4, &dinit)) return rc;
+            k_f64_to_f32_pad<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const double*)dinit64, ola, (float*)dinit, ola);
+            ctx->launches++;
+            io.init32 = (const float*)dinit;
+        }
+    }
+    const bool all64 = lead == cfg->gl_iters;
+    if (all64) io.out64 = (double*)dout64; else io.out32 = (float*)dout;
+    if (int rc = from_mel_dev_impl<double>(ctx, cfg, (const double*)dmel, 1, n_frames, io, seed, ola)) return rc;
+    if (!all64) {
+        k_f32_to_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const float*)dout, (double*)dout64, ola, 1.0);
         ctx->launches++;
     }
-    if (int rc = from_mel_dev_impl<double>(ctx, cfg, (const double*)dmel, 1, n_frames, (const float*)dinit, seed, ola, (float*)dout))
-        return rc;
-    k_f32_to_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const float*)dout, (double*)dout64, ola, 1.0);
-    ctx->launches++;
     CU(cudaMemcpyAsync(wav_out, dout64, (size_t)ola * 8, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return 0;
@@ -939,10 +1142,22 @@ int gomel_last_hot_kernel_ms(gomel_ctx* ctx, float* ms, int* launches)
     if (!ctx || !ms || !launches) return GOMEL_E_ARG;
     Guard g(ctx);
     *ms = 0.f; *launches = 0;
-    if (ctx->hot_launches <= 0) return fail(ctx, GOMEL_E_STATE, "no transform has run on this context yet");
+    if (ctx->hot_launches <= 0) return ctx->lead_launches > 0 ? 0 : fail(ctx, GOMEL_E_STATE, "no transform has run on this context yet");
     CU(cudaEventSynchronize(ctx->ev_k1));
     CU(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
     *launches = ctx->hot_launches;
+    return 0;
+}
+
+int gomel_last_lead_kernel_ms(gomel_ctx* ctx, float* ms, int* launches)
+{
+    if (!ctx || !ms || !launches) return GOMEL_E_ARG;
+    Guard g(ctx);
+    *ms = 0.f; *launches = 0;
+    if (ctx->lead_launches <= 0) return 0;
+    CU(cudaEventSynchronize(ctx->ev_l1));
+    CU(cudaEventElapsedTime(ms, ctx->ev_l0, ctx->ev_l1));
+    *launches = ctx->lead_launches;
     return 0;
 }
 
@@ -972,7 +1187,10 @@ int gomel_from_mel_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_m
 {
     if (!ctx) return GOMEL_E_ARG;
     Guard g(ctx);
-    return from_mel_dev_impl<float>(ctx, cfg, d_mel, n_clips, n_frames, d_init, seed, sig_stride, d_out);
+    GlIO io;
+    io.init32 = d_init; io.out32 = d_out;
+    if (cfg && (cfg->flags & GOMEL_FLAG_F64_REF)) return fail(ctx, GOMEL_E_UNSUPPORTED, "GOMEL_FLAG_F64_REF is a host-buffer test path");
+    return from_mel_dev_impl<float>(ctx, cfg, d_mel, n_clips, n_frames, io, seed, sig_stride);
 }
 int gomel_from_phase_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d_spec, int n_clips, long n_frames,
                          long sig_stride, float* d_out)
@@ -982,38 +1200,68 @@ int gomel_from_phase_dev(gomel_ctx* ctx, const gomel_config* cfg, const float* d
     return from_phase_dev_impl(ctx, cfg, d_spec, n_clips, n_frames, sig_stride, d_out);
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------- pipelined host batches
-// chunk c uses buffer set c&1; H2D on st_h2d, kernels on st, D2H on st_d2h, ordered by events
+// chunk c uses buffer set c % 3; H2D on st_h2d, magnitudes / start signals on st_pre, iterations on st (+ the
+// group streams), D2H on st_d2h, ordered by events.  Three sets: the copy-out of chunk c may still run while chunk
+// c+2 computes, so compute never waits for the host link unless the link is the bottleneck over a whole chunk.
+namespace {
+struct PipeEvents {
+    cudaEvent_t up[kPipeSets] = {}, done[kPipeSets] = {}, down[kPipeSets] = {}, pre[kPipeSets] = {};
+    cudaError_t create()
+    {
+        for (int b = 0; b < kPipeSets; b++)
+            for (cudaEvent_t* e : { &up[b], &done[b], &down[b], &pre[b] }) {
+                const cudaError_t rc = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+                if (rc != cudaSuccess) return rc;
+            }
+        return cudaSuccess;
+    }
+    ~PipeEvents()
+    {
+        for (int b = 0; b < kPipeSets; b++)
+            for (cudaEvent_t e : { up[b], done[b], down[b], pre[b] }) if (e) cudaEventDestroy(e);
+    }
+};
+// first CUDA error of a pipelined loop; later calls are skipped
+struct CudaChain {
+    cudaError_t err = cudaSuccess; const char* what = "";
+    bool operator()(cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; } return err == cudaSuccess; }
+    bool ok() const { return err == cudaSuccess; }
+};
+#define CH(call) chain((call), #call)
+}  // namespace
+
 static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
                                     const float* init, unsigned long long seed, void* out, int clips_per_chunk, bool pcm16)
 {
     Geo geo;
     if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     if (!mel || !out || n_clips <= 0 || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
+    if (cfg->flags & GOMEL_FLAG_F64_REF) return fail(ctx, GOMEL_E_UNSUPPORTED, "GOMEL_FLAG_F64_REF is a host-buffer test path");
     const long ola = geo.ola(n_frames);
     const long mel_per = n_frames * 2L * cfg->n_mels;
     int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
     if (cpc > n_clips) cpc = n_clips;
     if (cfg->gl_iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
-    void *dmel[2], *dinit[2] = { nullptr, nullptr }, *dout[2], *dpcm[2] = { nullptr, nullptr }, *dmags[2];
-    for (int b = 0; b < 2; b++) {
-        // per-chunk magnitudes and (when the caller injects none) start signals have buffers of their own, so the
-        // next chunk's are produced on st_pre while this chunk iterates: HBM-bound work under FP32-bound work
-        if (int rc = ensure(ctx, S_PM0 + b, (size_t)cpc * n_frames * kMagStride * 4, &dmags[b])) return rc;
-        if (!init) { if (int rc = ensure(ctx, S_PI0 + b, (size_t)cpc * ola * 4, &dinit[b])) return rc; }
-        if (int rc = ensure(ctx, S_CH0 + b, (size_t)cpc * mel_per * 4, &dmel[b])) return rc;
-        if (int rc = ensure(ctx, S_CH2 + b, (size_t)cpc * ola * 4, &dout[b])) return rc;
-        if (init) { if (int rc = ensure(ctx, S_CH4 + b, (size_t)cpc * ola * 4, &dinit[b])) return rc; }
-        if (pcm16) { if (int rc = ensure(ctx, S_CH6 + b, (size_t)cpc * ola * 2, &dpcm[b])) return rc; }
+    const int lead = lead_iters(ctx, cfg, geo);
+    const bool need32 = cfg->gl_iters - lead > 0, need64 = lead > 0;
+    void *dmel[kPipeSets], *dinit[kPipeSets], *dout[kPipeSets], *dpcm[kPipeSets] = {}, *dm32[kPipeSets] = {}, *dm64[kPipeSets] = {};
+    for (int b = 0; b < kPipeSets; b++) {
+        // per-chunk magnitudes and start signals have buffers of their own, so the next chunk's are produced on
+        // st_pre while this chunk iterates: HBM-bound work under FP32-bound work
+        if (need32) { if (int rc = ensure(ctx, pipe_slot(b, P_MAGS32), (size_t)cpc * n_frames * kMagStride * 4, &dm32[b])) return rc; }
+        if (need64) { if (int rc = ensure(ctx, pipe_slot(b, P_MAGS64), (size_t)cpc * n_frames * kMagStride * 8, &dm64[b])) return rc; }
+        if (int rc = ensure(ctx, pipe_slot(b, P_INIT), (size_t)cpc * ola * 4, &dinit[b])) return rc;
+        if (int rc = ensure(ctx, pipe_slot(b, P_IN), (size_t)cpc * mel_per * 4, &dmel[b])) return rc;
+        if (int rc = ensure(ctx, pipe_slot(b, P_OUT), (size_t)cpc * ola * 4, &dout[b])) return rc;
+        if (pcm16) { if (int rc = ensure(ctx, pipe_slot(b, P_PCM), (size_t)cpc * ola * 2, &dpcm[b])) return rc; }
     }
-    cudaEvent_t up[2], done[2], down[2], pre[2];
-    for (int b = 0; b < 2; b++) {
-        CU(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&pre[b], cudaEventDisableTiming));
-    }
-    int rc = 0;
+    // the iteration scratch is sized for a full chunk up front: no reallocation (= device synchronisation) mid-pipeline
+    if (int rc = gl_reserve(ctx, cfg, cpc, n_frames, ola, false)) return rc;
+    PipeEvents ev;
+    CU(ev.create());
     // chunk schedule: a small first chunk (short pipeline fill), full chunks, then a taper down to 64 clips (GOMEL_CHUNK_TAPER_MIN)
     // (short drain: the last D2H is the only copy that cannot overlap compute)
     std::vector<int> sizes;
@@ -1039,16 +1287,20 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         push(left);
     }
     const int n_chunks = (int)sizes.size();
-    int c0 = 0;
-    for (int c = 0; c < n_chunks && !rc; c0 += sizes[c], c++) {
-        const int b = c & 1, nc = sizes[c];
-        if (c >= 2) cudaStreamWaitEvent(ctx->st_h2d, done[b], 0);        // inputs of chunk c-2 consumed
-        cudaMemcpyAsync(dmel[b], mel + (size_t)c0 * mel_per, (size_t)nc * mel_per * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
-        if (init) cudaMemcpyAsync(dinit[b], init + (size_t)c0 * ola, (size_t)nc * ola * 4, cudaMemcpyHostToDevice, ctx->st_h2d);
-        cudaEventRecord(up[b], ctx->st_h2d);
-        cudaStreamWaitEvent(ctx->st_pre, up[b], 0);
-        if (c >= 2) cudaStreamWaitEvent(ctx->st_pre, done[b], 0);        // chunk c-2 no longer reads dmags[b] / dinit[b]
-        rc = mags_dev<float>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (float*)dmags[b], ctx->st_pre);
+    int rc = 0, c0 = 0;
+    CudaChain chain;
+    for (int c = 0; c < n_chunks && !rc && chain.ok(); c0 += sizes[c], c++) {
+        const int b = c % kPipeSets, nc = sizes[c];
+        if (c >= kPipeSets) CH(cudaStreamWaitEvent(ctx->st_h2d, ev.done[b], 0));   // inputs of chunk c-3 consumed
+        CH(cudaMemcpyAsync(dmel[b], mel + (size_t)c0 * mel_per, (size_t)nc * mel_per * 4, cudaMemcpyHostToDevice, ctx->st_h2d));
+        if (init) CH(cudaMemcpyAsync(dinit[b], init + (size_t)c0 * ola, (size_t)nc * ola * 4, cudaMemcpyHostToDevice, ctx->st_h2d));
+        CH(cudaEventRecord(ev.up[b], ctx->st_h2d));
+        CH(cudaStreamWaitEvent(ctx->st_pre, ev.up[b], 0));
+        if (c >= kPipeSets) CH(cudaStreamWaitEvent(ctx->st_pre, ev.done[b], 0));    // chunk c-3 no longer reads dmags[b] / dinit[b]
+        if (!chain.ok()) break;
+        GlIO io;
+        if (need32) { rc = mags_dev<float, float>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (float*)dm32[b], ctx->st_pre); io.mags32 = (const float*)dm32[b]; }
+        if (!rc && need64) { rc = mags_dev<float, double>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (double*)dm64[b], ctx->st_pre); io.mags64 = (const double*)dm64[b]; }
         if (!rc && !init) {
             // indexed by the sample's position in the whole batch: the start signals do not depend on the chunking
             // and equal those of gomel_from_mel_dev(seed) on the same batch
@@ -1056,30 +1308,36 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
                                                                                  (long)c0 * ola);
             ctx->launches++;
         }
-        cudaEventRecord(pre[b], ctx->st_pre);
-        cudaStreamWaitEvent(ctx->st, pre[b], 0);
-        if (c >= 2) cudaStreamWaitEvent(ctx->st, down[b], 0);            // output buffer of chunk c-2 drained
-        if (!rc) rc = gl_dev(ctx, cfg, (const float*)dmags[b], nc, n_frames, (const float*)dinit[b],
-                             seed + (unsigned long long)c0, ola, (float*)dout[b]);
-        if (pcm16 && !rc) {
+        if (rc) break;
+        CH(cudaEventRecord(ev.pre[b], ctx->st_pre));
+        CH(cudaStreamWaitEvent(ctx->st, ev.pre[b], 0));
+        if (c >= kPipeSets) CH(cudaStreamWaitEvent(ctx->st, ev.down[b], 0));        // output buffer of chunk c-3 drained
+        if (!chain.ok()) break;
+        io.init32 = (const float*)dinit[b]; io.out32 = (float*)dout[b];
+        rc = gl_dev(ctx, cfg, io, nc, n_frames, seed + (unsigned long long)c0, ola);
+        if (rc) break;
+        if (pcm16) {
             k_f32_to_pcm16<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st>>>((const float*)dout[b], (short*)dpcm[b], (long)nc * ola);
             ctx->launches++;
         }
-        cudaEventRecord(done[b], ctx->st);
-        cudaStreamWaitEvent(ctx->st_d2h, done[b], 0);
+        CH(cudaEventRecord(ev.done[b], ctx->st));
+        CH(cudaStreamWaitEvent(ctx->st_d2h, ev.done[b], 0));
         if (pcm16)
-            cudaMemcpyAsync((short*)out + (size_t)c0 * ola, dpcm[b], (size_t)nc * ola * 2, cudaMemcpyDeviceToHost, ctx->st_d2h);
+            CH(cudaMemcpyAsync((short*)out + (size_t)c0 * ola, dpcm[b], (size_t)nc * ola * 2, cudaMemcpyDeviceToHost, ctx->st_d2h));
         else
-            cudaMemcpyAsync((float*)out + (size_t)c0 * ola, dout[b], (size_t)nc * ola * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
-        cudaEventRecord(down[b], ctx->st_d2h);
+            CH(cudaMemcpyAsync((float*)out + (size_t)c0 * ola, dout[b], (size_t)nc * ola * 4, cudaMemcpyDeviceToHost, ctx->st_d2h));
+        CH(cudaEventRecord(ev.down[b], ctx->st_d2h));
     }
-    cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_pre); cudaStreamSynchronize(ctx->st);
-    cudaStreamSynchronize(ctx->st_d2h);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); cudaEventDestroy(pre[b]); }
+    // one exit path: drain every stream whatever happened, then report the first failure
+    CH(cudaStreamSynchronize(ctx->st_h2d)); CH(cudaStreamSynchronize(ctx->st_pre)); CH(cudaStreamSynchronize(ctx->st));
+    CH(cudaStreamSynchronize(ctx->st_d2h));
     if (rc) return rc;
+    if (!chain.ok()) return fail(ctx, GOMEL_E_CUDA, std::string(chain.what) + ": " + cudaGetErrorString(chain.err));
     CU(cudaGetLastError());
     return 0;
 }
+
+extern "C" {
 
 int gomel_from_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float* mel, int n_clips, long n_frames,
                               const float* init, unsigned long long seed, float* out, int clips_per_chunk)
@@ -1111,37 +1369,36 @@ int gomel_to_mel_batch_host(gomel_ctx* ctx, const gomel_config* cfg, const float
     const long mel_per = fr * 2L * cfg->n_mels;
     int cpc = clips_per_chunk > 0 ? clips_per_chunk : 64;
     if (cpc > n_clips) cpc = n_clips;
-    void *dsig[2], *dout[2];
-    for (int b = 0; b < 2; b++) {
-        if (int rc = ensure(ctx, S_CH0 + b, (size_t)cpc * stride * 4, &dsig[b])) return rc;
-        if (int rc = ensure(ctx, S_CH2 + b, (size_t)cpc * mel_per * 4, &dout[b])) return rc;
+    void *dsig[kPipeSets], *dout[kPipeSets];
+    for (int b = 0; b < kPipeSets; b++) {
+        if (int rc = ensure(ctx, pipe_slot(b, P_IN), (size_t)cpc * stride * 4, &dsig[b])) return rc;
+        if (int rc = ensure(ctx, pipe_slot(b, P_OUT), (size_t)cpc * mel_per * 4, &dout[b])) return rc;
         CU(cudaMemsetAsync(dsig[b], 0, (size_t)cpc * stride * 4, ctx->st_h2d));   // pad() zeros, written once
     }
-    cudaEvent_t up[2], done[2], down[2];
-    for (int b = 0; b < 2; b++) {
-        CU(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
-    }
+    PipeEvents ev;
+    CU(ev.create());
     int rc = 0;
+    CudaChain chain;
     const int n_chunks = (n_clips + cpc - 1) / cpc;
-    for (int c = 0; c < n_chunks && !rc; c++) {
-        const int b = c & 1, c0 = c * cpc, nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
-        if (c >= 2) cudaStreamWaitEvent(ctx->st_h2d, done[b], 0);
-        cudaMemcpy2DAsync(dsig[b], (size_t)stride * 4, wav + (size_t)c0 * n_samples, (size_t)n_samples * 4,
-                          (size_t)n_samples * 4, nc, cudaMemcpyHostToDevice, ctx->st_h2d);
-        cudaEventRecord(up[b], ctx->st_h2d);
-        cudaStreamWaitEvent(ctx->st, up[b], 0);
-        if (c >= 2) cudaStreamWaitEvent(ctx->st, down[b], 0);
+    for (int c = 0; c < n_chunks && !rc && chain.ok(); c++) {
+        const int b = c % kPipeSets, c0 = c * cpc, nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+        if (c >= kPipeSets) CH(cudaStreamWaitEvent(ctx->st_h2d, ev.done[b], 0));
+        CH(cudaMemcpy2DAsync(dsig[b], (size_t)stride * 4, wav + (size_t)c0 * n_samples, (size_t)n_samples * 4,
+                             (size_t)n_samples * 4, nc, cudaMemcpyHostToDevice, ctx->st_h2d));
+        CH(cudaEventRecord(ev.up[b], ctx->st_h2d));
+        CH(cudaStreamWaitEvent(ctx->st, ev.up[b], 0));
+        if (c >= kPipeSets) CH(cudaStreamWaitEvent(ctx->st, ev.down[b], 0));
+        if (!chain.ok()) break;
         rc = fwd_dev(ctx, cfg, MODE_MEL, (const float*)dsig[b], nc, stride, np, fr, (float*)dout[b]);
-        cudaEventRecord(done[b], ctx->st);
-        cudaStreamWaitEvent(ctx->st_d2h, done[b], 0);
-        cudaMemcpyAsync(mel_out + (size_t)c0 * mel_per, dout[b], (size_t)nc * mel_per * 4, cudaMemcpyDeviceToHost, ctx->st_d2h);
-        cudaEventRecord(down[b], ctx->st_d2h);
+        if (rc) break;
+        CH(cudaEventRecord(ev.done[b], ctx->st));
+        CH(cudaStreamWaitEvent(ctx->st_d2h, ev.done[b], 0));
+        CH(cudaMemcpyAsync(mel_out + (size_t)c0 * mel_per, dout[b], (size_t)nc * mel_per * 4, cudaMemcpyDeviceToHost, ctx->st_d2h));
+        CH(cudaEventRecord(ev.down[b], ctx->st_d2h));
     }
-    cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_d2h);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); }
+    CH(cudaStreamSynchronize(ctx->st_h2d)); CH(cudaStreamSynchronize(ctx->st)); CH(cudaStreamSynchronize(ctx->st_d2h));
     if (rc) return rc;
+    if (!chain.ok()) return fail(ctx, GOMEL_E_CUDA, std::string(chain.what) + ": " + cudaGetErrorString(chain.err));
     CU(cudaGetLastError());
     return 0;
 }
@@ -1260,7 +1517,7 @@ int gomel_ts_load(gomel_ts* ts, const float* d_mel_local, const float* d_init_lo
     if (!ts || !d_mel_local) return GOMEL_E_ARG;
     gomel_ctx* ctx = ts->ctx;
     Guard g(ctx);
-    if (int rc = mags_dev<float>(ctx, &ts->cfg, d_mel_local, ts->n_local, ts->mags)) return rc;
+    if (int rc = mags_dev<float, float>(ctx, &ts->cfg, d_mel_local, ts->n_local, ts->mags)) return rc;
     if (d_init_local) CU(cudaMemcpyAsync(ts->sig[0], d_init_local, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
     else {
         k_fill_uniform<<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(ts->sig[0], ts->n_samples, seed, ts->sample_begin);

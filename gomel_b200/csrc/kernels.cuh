@@ -374,8 +374,10 @@ constexpr int kMagsRowsPerPass = 4;       // frames handled together by one CTA 
 // FS = 8 (Resolut 2048): bin k' of the 2048-point transform sits where bin 2k' of the 4096-point core is read,
 // the odd core bins are zero, and the scale is 1/2048 (the core's unnormalised inverse of the even-bin spectrum
 // is 2048 times the reference's IFFT).
-template <typename T, int FS = 16>
-__global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel, float* __restrict__ mags,
+// OUT = float: the float32 iteration kernel's rows.  OUT = double: the float64 lead iterations' rows (gl_f64.cuh):
+// the reference's own division by TuneMul, then the exact power-of-two scale.
+template <typename T, int FS = 16, typename OUT = float>
+__global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel, OUT* __restrict__ mags,
                                                        const int* __restrict__ inv_lo, const int* __restrict__ inv_hi,
                                                        const double* __restrict__ inv_mod, int n_mels,
                                                        double tune_add, double tune_mul, long n_rows)
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
         for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes in mag_pos order
             const int kc = mag_unpos(pos);
             if (FS == 8 && (kc & 1)) {
-                for (int r = 0; r < nr; r++) mags[(row0 + r) * kMagStride + pos] = 0.0f;
+                for (int r = 0; r < nr; r++) mags[(row0 + r) * kMagStride + pos] = (OUT)0;
                 continue;
             }
             const int i = kc >> (FS == 16 ? 0 : 1);
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
             const double md = lerp ? inv_mod[i] : 0.0;
             for (int r = 0; r < nr; r++) {
                 const double* er = e + r * per_row;
-                float* out = mags + (row0 + r) * kMagStride;
+                OUT* out = mags + (row0 + r) * kMagStride;
                 const int nch = (i == FS * 128 - 1) ? 2 : 1;
                 for (int l = 0; l < nch; l++) {
                     double total = 0.0;
@@ -415,8 +417,10 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                         for (int k = lo; k < hi; k++) total += er[2 * k + l];
                         total /= (double)(hi - lo + 1);
                     }
-                    const double v = fabs((total - tune_add) * scale);
-                    out[l ? 2048 : pos] = (float)v;
+                    const double v = std::is_same<OUT, double>::value
+                                         ? fabs((total - tune_add) / tune_mul) * (1.0 / (256.0 * FS))
+                                         : fabs((total - tune_add) * scale);
+                    out[l ? 2048 : pos] = (OUT)v;
                 }
             }
         }

@@ -43,14 +43,17 @@ class Mel:
         self.Device = 0
         self.InitSignal = None      # ola_len float64 replacing rand.Float64() (mel/mel.go:80-83)
         self.Seed = None
-        self.Strict = False         # True: float64 Griffin-Lim (GOMEL_FLAG_F64) -- the parity instrument
+        # Griffin-Lim precision.  False (default): the library's float64 lead iterations, then float32;
+        # True: every iteration in float64 on the fused kernel (GOMEL_FLAG_F64); "ref": the round-1 strict
+        # float64 path (GOMEL_FLAG_F64_REF), a slow test instrument
+        self.Strict = False
 
     # ---- plumbing
     def _cfg(self):
         return _lib.make_config(n_fft=self.Resolut, hop=self.Window, n_mels=self.NumMels, n_freqs=0,
                                 gl_iters=self.GriffinLimIterations, tune_mul=self.TuneMul,
                                 tune_add=self.TuneAdd, volume_boost=self.VolumeBoost,
-                                flags=_lib.FLAG_F64 if self.Strict else 0)
+                                flags=(_lib.FLAG_F64_REF if self.Strict == "ref" else _lib.FLAG_F64) if self.Strict else 0)
 
     def _ctx(self, cfg):
         ctx = _lib.default_context(self.Device)
@@ -91,10 +94,10 @@ class Mel:
             raise ErrFileNotLoaded()
         ospectrum = self.ToMel(buf)
         codec.mel_dump_image(outputFile, ospectrum, self.NumMels, self.YReverse,
-                             float(len(buf) * self.NumMels) / float(len(ospectrum)), float(sr))
+                             float(len(buf) * self.NumMels) / float(len(ospectrum)), float(sr), device=self.Device)
 
     def ToWavPng(self, inputFile, outputFile):
-        buf, samples, samplerate = codec.mel_load_png(inputFile, self.YReverse)
+        buf, samples, samplerate = codec.mel_load_png(inputFile, self.YReverse, device=self.Device)
         if len(buf) == 0:
             raise ErrFileNotLoaded()
         buf += self.VolumeBoost                                   # mel/mel.go:218-221 (additive, log domain)

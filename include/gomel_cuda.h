@@ -54,11 +54,18 @@ typedef struct {
                             registered tables for this (n_fft, n_mels). */
 } gomel_config;
 
-/* STRICT mode for gomel_from_mel: the whole Griffin-Lim loop in float64 (kernels_f64.cuh).  Griffin-Lim is
- * ill-conditioned: float32 lands 7e-6 .. 3e-4 from the float64 reference after 32 iterations on a 10 s
- * clip depending on the start signal; this path reproduces the reference to ~1e-12 for any start signal,
- * at a fraction of the float32 throughput.  Host-buffer API only. */
+/* Precision of the Griffin-Lim loop (mel.ISTFT, mel/mel.go:76-139).  The loop is ill-conditioned in its FIRST
+ * iterations only: a rounding error made in iteration 0-1 ends ~300x larger after 32 iterations, one made after
+ * iteration ~8 does not grow (profiles/r02_gl_parity_sweep.md).  Default: the first `lead` iterations (4, see
+ * gomel_set_lead_f64) run in float64 end to end (gl_f64.cuh), the rest in float32 -- within 1e-4 of the float64
+ * reference for every start signal tried, where an all-float32 loop lands between 7e-6 and 3e-4.
+ *   GOMEL_FLAG_F64      every iteration in float64 on the fused kernel (all from_mel entry points; the host-buffer
+ *                       call then also reads the start signal and returns the waveform without a float32 step).
+ *   GOMEL_FLAG_F64_REF  gomel_from_mel only: the round-1 strict path (one frame pair per CTA, spectra through HBM,
+ *                       frames added in the reference's own order) -- a slow test instrument pinned < 1e-10 to
+ *                       the oracle; the other two modes are checked against it. */
 #define GOMEL_FLAG_F64 1
+#define GOMEL_FLAG_F64_REF 2
 
 /* ---- context ------------------------------------------------------------------------- */
 int  gomel_ctx_create(int device, gomel_ctx **out);
@@ -69,6 +76,9 @@ const char *gomel_version(void);
 unsigned long long gomel_launch_count(gomel_ctx *ctx);
 /* frames per tile for the tiled kernels; 0 = automatic (default) */
 int  gomel_set_tile_frames(gomel_ctx *ctx, int tile_frames);
+/* number of leading Griffin-Lim iterations run in float64 (default 4, env GOMEL_LEAD_F64; 0 = all float32 as in
+ * round 1; values >= GriffinLimIterations behave like GOMEL_FLAG_F64).  Returns the previous value. */
+int  gomel_set_lead_f64(gomel_ctx *ctx, int lead_iters);
 
 /* ---- sizing: pad (mel/impl.go:429-455) + gossp NumFrames + ISTFT length (mel/mel.go:79) --- */
 int  gomel_frames(const gomel_config *cfg, long n_samples, long *n_padded, long *n_frames, long *ola_len);
@@ -137,6 +147,8 @@ int  gomel_timer_stop(gomel_ctx *ctx, float *ms);                     /* records
  * Griffin-Lim iteration launches of a FromMel, or the STFT launch of a ToMel/ToPhase), measured
  * by CUDA events recorded around those launches on the context's stream; *launches = how many. */
 int  gomel_last_hot_kernel_ms(gomel_ctx *ctx, float *ms, int *launches);
+/* same for the float64 lead iterations of the last Griffin-Lim run (*launches = 0, *ms = 0 if there were none) */
+int  gomel_last_lead_kernel_ms(gomel_ctx *ctx, float *ms, int *launches);
 
 /* Batched STFT + mel (K1+K2).  d_sig: [n_clips][sig_stride] float32, each clip zero padded to
  * n_padded = sig_len samples; d_mel: [n_clips][n_frames][n_mels][2] float32 (natural log). */
