@@ -43,6 +43,7 @@ SIGNATURES = {
     "gomel_launch_count": (C.c_ulonglong, [_vp]),
     "gomel_set_tile_frames": (C.c_int, [_vp, C.c_int]),
     "gomel_set_lead_f64": (C.c_int, [_vp, C.c_int]),
+    "gomel_set_f32_tail": (C.c_int, [_vp, C.c_int]),
     "gomel_frames": (C.c_int, [_cp, C.c_long, _lp, _lp, _lp]),
     "gomel_ola_len": (C.c_long, [_cp, C.c_long]),
     "gomel_set_mel_tables": (C.c_int, [_vp, _cp, _ip, _ip, _dp, _ip, _ip, _dp]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "gomel_ts_load": (C.c_int, [_vp, _vp, _vp, C.c_ulonglong]),
     "gomel_ts_iterate": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gomel_ts_halo_ptrs": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "gomel_ts_halo_elem_bytes": (C.c_int, [_vp, C.c_int]),
+    "gomel_ts_lead_iters": (C.c_int, [_vp]),
     "gomel_ts_comm_stream": (_vp, [_vp]),
     "gomel_ts_comm_begin": (C.c_int, [_vp, C.c_int]),
     "gomel_ts_comm_end": (C.c_int, [_vp, C.c_int]),
@@ -248,11 +251,22 @@ class Context:
         self.check(self.lib.gomel_set_tile_frames(self.h, int(t)))
 
     def set_lead_f64(self, k):
-        """float64 lead iterations of Griffin-Lim (default 4); returns the previous value"""
+        """minimum number of float64 lead iterations of Griffin-Lim (default 4); returns the previous value"""
         rc = self.lib.gomel_set_lead_f64(self.h, int(k))
         if rc < 0:
             self.check(rc)
         return rc
+
+    def set_f32_tail(self, n):
+        """maximum number of trailing float32 iterations (default 28; < 0 unlimited); returns the previous value"""
+        rc = self.lib.gomel_set_f32_tail(self.h, int(n))
+        if rc < 0:
+            self.check(rc)
+        return -1 if rc == 0x7fffffff else rc
+
+    def set_gl_precision(self, lead, tail):
+        """-> (previous lead, previous tail)"""
+        return self.set_lead_f64(lead), self.set_f32_tail(tail)
 
     # ---- host-buffer API -------------------------------------------------------------
     def to_mel(self, cfg, wav):

@@ -56,7 +56,10 @@ enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64
 constexpr int kPipeSets = 3;
 enum PipeKind { P_IN = 0, P_OUT, P_INIT, P_PCM, P_MAGS32, P_MAGS64 };
 constexpr int pipe_slot(int set, int kind) { return S_PIPE + set * 8 + kind; }
-constexpr int kDefaultLeadF64 = 4;           // Griffin-Lim iterations run in float64 before the float32 ones
+// Griffin-Lim precision policy (profiles/r02_gl_parity_sweep.md): at least kDefaultLeadF64 float64 iterations
+// first, and at most kDefaultF32Tail float32 iterations at the end -> lead = max(4, iters - 28)
+constexpr int kDefaultLeadF64 = 4;
+constexpr int kDefaultF32Tail = 28;
 
 }  // namespace
 
@@ -74,6 +77,7 @@ struct gomel_ctx {
     int hot_launches = 0;     // launches of the dominant kernel bracketed by ev_k0/ev_k1
     int lead_launches = 0;    // float64 lead iterations of the last Griffin-Lim, bracketed by ev_l0/ev_l1
     int lead_f64 = kDefaultLeadF64;   // gomel_set_lead_f64 / GOMEL_LEAD_F64
+    int f32_tail = kDefaultF32Tail;   // gomel_set_f32_tail / GOMEL_F32_TAIL; < 0: unlimited
     double* d_tables_d64 = nullptr;   // gl_f64.cuh tables (built on first use)
     float4* d_tables = nullptr;
     float4* d_tables_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
@@ -351,7 +355,9 @@ int lead_iters(const gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo)
     if (geo.alt) return 0;
     const int iters = cfg->gl_iters < 0 ? 0 : cfg->gl_iters;
     if (cfg->flags & GOMEL_FLAG_F64) return iters;
-    return ctx->lead_f64 < iters ? ctx->lead_f64 : iters;
+    int lead = ctx->lead_f64;
+    if (ctx->f32_tail >= 0 && iters - ctx->f32_tail > lead) lead = iters - ctx->f32_tail;
+    return lead < iters ? lead : iters;
 }
 
 // Buffers of one Griffin-Lim run.  Exactly one of out32 / out64 is set (out64 only when every iteration is
@@ -487,7 +493,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
             const long c0 = c_lo(g), nc = c_lo(g + 1) - c0;
             if (tl.n_tiles > 1) {
                 d64::k_halo_fix_f64<<<(unsigned)(nc * (tl.n_tiles - 1)), 256, 0, gs[g]>>>(
-                    fin + c0 * sig_stride, hb[(lead - 1) & 1] + c0 * hb_tiles * geo.halo, tl, geo.hop, geo.halo, 1, hb_tiles);
+                    fin + c0 * sig_stride, hb[(lead - 1) & 1] + c0 * hb_tiles * geo.halo, tl, geo.hop, geo.halo, 1, hb_tiles, tl.n_tiles);
                 ctx->launches++;
             }
             if (conv) {
@@ -744,6 +750,7 @@ int gomel_ctx_create(int device, gomel_ctx** out)
             const int v = atoi(e);
             if (v >= 0) ctx->lead_f64 = v;
         }
+        if (const char* e = getenv("GOMEL_F32_TAIL")) ctx->f32_tail = atoi(e) < 0 ? -1 : atoi(e);   // trailing float32 iterations, < 0 unlimited
         std::vector<float> blob;
         build_fft_tables(blob);
         CU(cudaMalloc(&ctx->d_tables, kTableBytes));
@@ -804,6 +811,15 @@ int gomel_set_lead_f64(gomel_ctx* ctx, int lead)
     const int prev = ctx->lead_f64;
     ctx->lead_f64 = lead;
     return prev;
+}
+
+int gomel_set_f32_tail(gomel_ctx* ctx, int tail)
+{
+    if (!ctx) return GOMEL_E_ARG;
+    Guard g(ctx);
+    const int prev = ctx->f32_tail;
+    ctx->f32_tail = tail < 0 ? -1 : tail;
+    return prev < 0 ? 0x7fffffff : prev;
 }
 
 int gomel_frames(const gomel_config* cfg, long n_samples, long* n_padded, long* n_frames, long* ola_len)
@@ -1415,6 +1431,9 @@ struct gomel_ts {
     Tiling tl;
     int ext_prev = 0, ext_next = 0;
     float *sig[2] = { nullptr, nullptr }, *hb[2] = { nullptr, nullptr }, *mags = nullptr;
+    // float64 lead iterations (same policy as the batch path: iterations [0, lead) run on k_gl_iter_f64)
+    int lead = 0;
+    double *sig64[2] = { nullptr, nullptr }, *hb64[2] = { nullptr, nullptr }, *mags64 = nullptr;
     cudaStream_t st_edge = nullptr, st_comm = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_int = nullptr, ev_comm = nullptr;
     bool have_edge = false, have_int = false, have_comm = false;
@@ -1464,14 +1483,24 @@ int gomel_ts_create2(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_tota
     ts->tl.edge_first = ef; ts->tl.edge_last = el;
     const long mid = ts->n_local - ef - el;
     ts->tl.n_tiles = (ef > 0) + (int)((mid + T - 1) / T) + (el > 0);
+    ts->lead = (cfg->flags & GOMEL_FLAG_F64) ? 0x7fffffff : lead_iters(ctx, cfg, Geo());
     auto boot = [&]() -> int {
         const size_t hb_bytes = (size_t)(ts->tl.n_tiles + 1) * kHalo * 4;
         for (int i = 0; i < 2; i++) {
             CU(cudaMalloc(&ts->sig[i], (size_t)ts->n_samples * 4));
             CU(cudaMalloc(&ts->hb[i], hb_bytes));
             CU(cudaMemsetAsync(ts->hb[i], 0, hb_bytes, ctx->st));
+            if (ts->lead > 0) {
+                CU(cudaMalloc(&ts->sig64[i], (size_t)ts->n_samples * 8));
+                CU(cudaMalloc(&ts->hb64[i], hb_bytes * 2));
+                CU(cudaMemsetAsync(ts->hb64[i], 0, hb_bytes * 2, ctx->st));
+            }
         }
         CU(cudaMalloc(&ts->mags, (size_t)ts->n_local * kMagStride * 4));
+        if (ts->lead > 0) {
+            CU(cudaMalloc(&ts->mags64, (size_t)ts->n_local * kMagStride * 8));
+            if (int rc = ensure_tables_d64(ctx)) return rc;
+        }
         CU(cudaStreamCreateWithFlags(&ts->st_edge, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ts->st_comm, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ts->ev_edge, cudaEventDisableTiming));
@@ -1492,8 +1521,8 @@ void gomel_ts_destroy(gomel_ts* ts)
     if (ts->st_edge) cudaStreamSynchronize(ts->st_edge);
     if (ts->st_comm) cudaStreamSynchronize(ts->st_comm);
     if (ts->nccl_comm && g_nccl_destroy) g_nccl_destroy(ts->nccl_comm);
-    for (int i = 0; i < 2; i++) { cudaFree(ts->sig[i]); cudaFree(ts->hb[i]); }
-    cudaFree(ts->mags);
+    for (int i = 0; i < 2; i++) { cudaFree(ts->sig[i]); cudaFree(ts->hb[i]); cudaFree(ts->sig64[i]); cudaFree(ts->hb64[i]); }
+    cudaFree(ts->mags); cudaFree(ts->mags64);
     if (ts->ev_edge) cudaEventDestroy(ts->ev_edge);
     if (ts->ev_int) cudaEventDestroy(ts->ev_int);
     if (ts->ev_comm) cudaEventDestroy(ts->ev_comm);
@@ -1518,13 +1547,38 @@ int gomel_ts_load(gomel_ts* ts, const float* d_mel_local, const float* d_init_lo
     gomel_ctx* ctx = ts->ctx;
     Guard g(ctx);
     if (int rc = mags_dev<float, float>(ctx, &ts->cfg, d_mel_local, ts->n_local, ts->mags)) return rc;
+    if (ts->lead > 0) { if (int rc = mags_dev<float, double>(ctx, &ts->cfg, d_mel_local, ts->n_local, ts->mags64)) return rc; }
     if (d_init_local) CU(cudaMemcpyAsync(ts->sig[0], d_init_local, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
     else {
         k_fill_uniform<<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(ts->sig[0], ts->n_samples, seed, ts->sample_begin);
         ctx->launches++;
     }
+    if (ts->lead > 0) {       // the float64 iterations start from the exact float32 start signal
+        k_f32_to_f64<<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(ts->sig[0], ts->sig64[0], ts->n_samples, 1.0);
+        ctx->launches++;
+    }
     ts->have_edge = ts->have_int = ts->have_comm = false;
     CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+// hand-over from the float64 lead iterations to the float32 ones (and the float64 form of gomel_ts_finish): fold
+// every halo partial of iteration `last_iter` in -- own tiles' heads, the previous rank's tail (already in sig[0..halo))
+// and the next rank's head partial over this rank's tail region -- then narrow to float32.  Runs on ctx->st.
+static int ts_fold_f64(gomel_ts* ts, int last_iter, float* dst32)
+{
+    gomel_ctx* ctx = ts->ctx;
+    if (ts->have_comm) CU(cudaStreamWaitEvent(ctx->st, ts->ev_comm, 0));
+    if (ts->have_edge) CU(cudaStreamWaitEvent(ctx->st, ts->ev_edge, 0));
+    double* fin = ts->sig64[(last_iter + 1) & 1];
+    const int t_first = ts->ext_prev ? 0 : 1, t_end = ts->tl.n_tiles + (ts->ext_next ? 1 : 0);
+    if (t_end > t_first) {
+        d64::k_halo_fix_f64<<<(unsigned)(t_end - t_first), 256, 0, ctx->st>>>(fin, ts->hb64[last_iter & 1], ts->tl, kHop, kHalo,
+                                                                            t_first, ts->tl.n_tiles + 1, t_end);
+        ctx->launches++;
+    }
+    d64::k_f64_to_f32<<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(fin, dst32, ts->n_samples);
+    ctx->launches++;
     return 0;
 }
 
@@ -1533,12 +1587,36 @@ int gomel_ts_iterate(gomel_ts* ts, int iter, int part)
     if (!ts || iter < 0 || part < 0 || part > 2) return GOMEL_E_ARG;
     gomel_ctx* ctx = ts->ctx;
     Guard g(ctx);
-    SynParams p = {};
-    p.tables = ctx->d_tables; p.tl = ts->tl; p.mags = ts->mags;
-    p.sig_in = ts->sig[iter & 1]; p.sig_out = ts->sig[(iter + 1) & 1];
-    p.hb_in = iter ? ts->hb[(iter + 1) & 1] : nullptr; p.hb_out = ts->hb[iter & 1];
-    p.hb_tiles = ts->tl.n_tiles + 1; p.ext_prev = ts->ext_prev; p.ext_next = ts->ext_next;
+    const bool f64 = iter < ts->lead;
     const int nt = ts->tl.n_tiles;
+    if (!f64 && iter == ts->lead && iter > 0 && part != 2) {
+        // first float32 iteration: its input is the folded, narrowed result of the last float64 iteration
+        if (int rc = ts_fold_f64(ts, iter - 1, ts->sig[iter & 1])) return rc;
+        CU(cudaEventRecord(ts->ev_int, ctx->st)); ts->have_int = true;
+    }
+    SynParams p = {};
+    d64::GLParams q = {};
+    if (f64) {
+        q.tables = ctx->d_tables_d64; q.tl = ts->tl; q.mags = ts->mags64;
+        q.sig_in = ts->sig64[iter & 1]; q.sig_out = ts->sig64[(iter + 1) & 1];
+        q.hb_in = iter ? ts->hb64[(iter + 1) & 1] : nullptr; q.hb_out = ts->hb64[iter & 1];
+        q.hb_tiles = nt + 1; q.ext_prev = ts->ext_prev; q.ext_next = ts->ext_next;
+    } else {
+        p.tables = ctx->d_tables; p.tl = ts->tl; p.mags = ts->mags;
+        p.sig_in = ts->sig[iter & 1]; p.sig_out = ts->sig[(iter + 1) & 1];
+        p.hb_in = (iter && iter != ts->lead) ? ts->hb[(iter + 1) & 1] : nullptr; p.hb_out = ts->hb[iter & 1];
+        p.hb_tiles = nt + 1; p.ext_prev = ts->ext_prev; p.ext_next = ts->ext_next;
+    }
+    auto launch = [&](int grid, cudaStream_t st, int tile_lo, int tiles, int edge_mode, int e0, int e1) {
+        if (f64) {
+            q.tile_lo = tile_lo; q.tiles_in_launch = tiles; q.edge_mode = edge_mode; q.edge_tile0 = e0; q.edge_tile1 = e1;
+            d64::k_gl_iter_f64<kHS><<<grid, kThreads, d64::kSmemBytes, st>>>(q);
+        } else {
+            p.tile_lo = tile_lo; p.tiles_in_launch = tiles; p.edge_mode = edge_mode; p.edge_tile0 = e0; p.edge_tile1 = e1;
+            k_gl_iter<kHS><<<grid, kThreads, kGlSmemBytes, st>>>(p);
+        }
+        ctx->launches++;
+    };
     // boundary tiles: tile 0 if a previous rank exists, tile nt-1 if a next rank exists
     int edges[2], n_edge = 0;
     if (ts->ext_prev) edges[n_edge++] = 0;
@@ -1547,29 +1625,19 @@ int gomel_ts_iterate(gomel_ts* ts, int iter, int part)
     if (part == 0) {
         if (ts->have_comm) CU(cudaStreamWaitEvent(ctx->st, ts->ev_comm, 0));
         if (ts->have_edge) CU(cudaStreamWaitEvent(ctx->st, ts->ev_edge, 0));
-        p.tile_lo = 0; p.tiles_in_launch = nt;
-        k_gl_iter<kHS><<<nt, kThreads, kGlSmemBytes, ctx->st>>>(p);
-        ctx->launches++;
+        launch(nt, ctx->st, 0, nt, 0, 0, 0);
         CU(cudaEventRecord(ts->ev_edge, ctx->st)); ts->have_edge = true;
         CU(cudaEventRecord(ts->ev_int, ctx->st)); ts->have_int = true;
     } else if (part == 1) {
         if (ts->have_int) CU(cudaStreamWaitEvent(ts->st_edge, ts->ev_int, 0));
         if (ts->have_comm) CU(cudaStreamWaitEvent(ts->st_edge, ts->ev_comm, 0));
-        if (n_edge > 0) {
-            p.edge_mode = 1; p.edge_tile0 = edges[0]; p.edge_tile1 = edges[n_edge - 1];
-            k_gl_iter<kHS><<<n_edge, kThreads, kGlSmemBytes, ts->st_edge>>>(p);
-            ctx->launches++;
-        }
+        if (n_edge > 0) launch(n_edge, ts->st_edge, 0, nt, 1, edges[0], edges[n_edge - 1]);
         CU(cudaEventRecord(ts->ev_edge, ts->st_edge)); ts->have_edge = true;
     } else {
         // interior of iteration `iter` needs the boundary tiles of iteration iter-1 (recorded before
         // this iteration's part-1 call re-records ev_edge; callers issue part 2 of iteration i-1
         // before part 1 of iteration i, so the wait below is enqueued by the previous part-1 call)
-        if (hi > lo) {
-            p.tile_lo = lo; p.tiles_in_launch = hi - lo;
-            k_gl_iter<kHS><<<hi - lo, kThreads, kGlSmemBytes, ctx->st>>>(p);
-            ctx->launches++;
-        }
+        if (hi > lo) launch(hi - lo, ctx->st, lo, hi - lo, 0, 0, 0);
         CU(cudaEventRecord(ts->ev_int, ctx->st)); ts->have_int = true;
         // the NEXT iteration's interior must not start before this iteration's boundary tiles finished
         if (ts->have_edge) CU(cudaStreamWaitEvent(ctx->st, ts->ev_edge, 0));
@@ -1581,6 +1649,15 @@ int gomel_ts_iterate(gomel_ts* ts, int iter, int part)
 int gomel_ts_halo_ptrs(gomel_ts* ts, int iter, float** send_tail, float** send_head, float** recv_tail, float** recv_head)
 {
     if (!ts || iter < 0) return GOMEL_E_ARG;
+    if (iter < ts->lead) {          // float64 iteration: the four pointers address 2816 DOUBLES each (gomel_ts_halo_elem_bytes)
+        double* out = ts->sig64[(iter + 1) & 1];
+        double* hbo = ts->hb64[iter & 1];
+        if (send_tail) *send_tail = ts->ext_next ? (float*)(out + ts->n_local * kHop) : nullptr;
+        if (recv_head) *recv_head = ts->ext_next ? (float*)(hbo + (long)ts->tl.n_tiles * kHalo) : nullptr;
+        if (send_head) *send_head = ts->ext_prev ? (float*)hbo : nullptr;
+        if (recv_tail) *recv_tail = ts->ext_prev ? (float*)out : nullptr;
+        return 0;
+    }
     float* out = ts->sig[(iter + 1) & 1];
     float* hbo = ts->hb[iter & 1];
     if (send_tail) *send_tail = ts->ext_next ? out + ts->n_local * kHop : nullptr;
@@ -1589,6 +1666,14 @@ int gomel_ts_halo_ptrs(gomel_ts* ts, int iter, float** send_tail, float** send_h
     if (recv_tail) *recv_tail = ts->ext_prev ? out : nullptr;
     return 0;
 }
+
+int gomel_ts_halo_elem_bytes(gomel_ts* ts, int iter)
+{
+    if (!ts || iter < 0) return GOMEL_E_ARG;
+    return iter < ts->lead ? 8 : 4;
+}
+
+int gomel_ts_lead_iters(gomel_ts* ts) { return ts ? ts->lead : GOMEL_E_ARG; }
 
 void* gomel_ts_comm_stream(gomel_ts* ts) { return ts ? (void*)ts->st_comm : nullptr; }
 
@@ -1620,6 +1705,11 @@ int gomel_ts_finish(gomel_ts* ts, int iters, float* d_out_local)
     CU(cudaStreamSynchronize(ts->st_edge));
     CU(cudaStreamSynchronize(ts->st_comm));
     CU(cudaStreamSynchronize(ctx->st));
+    if (iters > 0 && iters <= ts->lead) {       // the last iteration was a float64 one
+        if (int rc = ts_fold_f64(ts, iters - 1, d_out_local)) return rc;
+        CU(cudaStreamSynchronize(ctx->st));
+        return 0;
+    }
     float* fin = ts->sig[iters & 1];
     const int t_first = ts->ext_prev ? 0 : 1;
     if (iters > 0 && ts->tl.n_tiles - t_first > 0) {
@@ -1755,11 +1845,12 @@ int gomel_ts_run_nccl(gomel_ts* ts, int first_iter, int n_iters, int overlap)
             float *send_tail, *send_head, *recv_tail, *recv_head;
             gomel_ts_halo_ptrs(ts, it, &send_tail, &send_head, &recv_tail, &recv_head);
             if (ts->world > 1) {
+                const int dt = it < ts->lead ? 8 /* ncclDouble */ : 7 /* ncclFloat */;
                 int rc = g_nccl.GroupStart();
-                if (!rc && send_head) rc = g_nccl.Send(send_head, kHalo, 7 /* ncclFloat */, ts->rank - 1, ts->nccl_comm, ts->st_comm);
-                if (!rc && recv_tail) rc = g_nccl.Recv(recv_tail, kHalo, 7, ts->rank - 1, ts->nccl_comm, ts->st_comm);
-                if (!rc && send_tail) rc = g_nccl.Send(send_tail, kHalo, 7, ts->rank + 1, ts->nccl_comm, ts->st_comm);
-                if (!rc && recv_head) rc = g_nccl.Recv(recv_head, kHalo, 7, ts->rank + 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && send_head) rc = g_nccl.Send(send_head, kHalo, dt, ts->rank - 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && recv_tail) rc = g_nccl.Recv(recv_tail, kHalo, dt, ts->rank - 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && send_tail) rc = g_nccl.Send(send_tail, kHalo, dt, ts->rank + 1, ts->nccl_comm, ts->st_comm);
+                if (!rc && recv_head) rc = g_nccl.Recv(recv_head, kHalo, dt, ts->rank + 1, ts->nccl_comm, ts->st_comm);
                 const int rc2 = g_nccl.GroupEnd();
                 if (rc || rc2) return fail(ctx, GOMEL_E_CUDA, std::string("NCCL halo exchange: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc ? rc : rc2) : "error"));
             }

@@ -417,11 +417,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
     }
 }
 
-// folds the head partials in: sig[s] += hb[s] over the head regions of tiles t_first .. n_tiles-1
+// folds the head partials in: sig[s] += hb[s] over the head regions of tiles t_first .. t_end-1 (t_end = n_tiles, or
+// n_tiles + 1 when slot n_tiles holds the next rank's head partial over this rank's tail region)
 __global__ void k_halo_fix_f64(double* __restrict__ sig, const double* __restrict__ hb, Tiling tl, int hop, int halo,
-                               int t_first, int hb_tiles)
+                               int t_first, int hb_tiles, int t_end)
 {
-    const int nt = tl.n_tiles - t_first;
+    const int nt = t_end - t_first;
     const int clip = blockIdx.x / nt, tile = blockIdx.x % nt + t_first;
     const long s0 = (long)tile_begin(tl, tile) * hop;
     double* __restrict__ d = sig + (long)clip * tl.sig_stride + s0;

@@ -78,6 +78,10 @@ class Session:
         self.ctx.check(self.ctx.lib.gomel_ts_halo_ptrs(self.h, it, *[C.byref(x) for x in p]))
         return dict(send_tail=p[0].value, send_head=p[1].value, recv_tail=p[2].value, recv_head=p[3].value)
 
+    def halo_elem_bytes(self, it):
+        """8 while iteration `it` is one of the float64 lead iterations (the halo pointers then address doubles), else 4"""
+        return int(self.ctx.lib.gomel_ts_halo_elem_bytes(self.h, it))
+
     def comm_begin(self, it):
         self.ctx.check(self.ctx.lib.gomel_ts_comm_begin(self.h, it))
 
@@ -106,8 +110,9 @@ class Session:
 class _DevArray:
     """zero-copy view of device memory for torch.as_tensor (CUDA array interface)."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, n, elem_bytes=4):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if elem_bytes == 8 else "<f4",
+                                         "data": (int(ptr), False), "version": 2}
 
 
 class NcclExchange:
@@ -121,13 +126,16 @@ class NcclExchange:
         self.stream = torch.cuda.ExternalStream(session.comm_stream, device=torch.device("cuda", session.ctx.device))
         self._cache = {}
 
-    def _ops(self, parity):
-        """P2P op list for iterations of this parity (the four halo pointers alternate between two buffer sets)"""
+    def _ops(self, it):
+        """P2P op list for iteration `it`: the four halo pointers alternate between two buffer sets, and the float64
+        lead iterations have buffer sets (and an element type) of their own"""
+        eb = self.s.halo_elem_bytes(it)
+        parity = (it & 1, eb)
         if parity not in self._cache:
             torch, dist, s = self.torch, self.dist, self.s
-            p = s.halo_ptrs(parity)
+            p = s.halo_ptrs(it)
             dev = torch.device("cuda", s.ctx.device)
-            t = lambda ptr: torch.as_tensor(_DevArray(ptr, HALO), device=dev)
+            t = lambda ptr: torch.as_tensor(_DevArray(ptr, HALO, eb), device=dev)
             ops = []
             if p["send_head"]:          # previous rank exists
                 ops.append(dist.P2POp(dist.isend, t(p["send_head"]), s.rank - 1, self.group))
@@ -140,7 +148,7 @@ class NcclExchange:
 
     def __call__(self, it):
         s = self.s
-        ops = self._ops(it & 1)
+        ops = self._ops(it)
         s.comm_begin(it)
         if ops:
             with self.torch.cuda.stream(self.stream):
@@ -198,14 +206,18 @@ def run_local(ctx, cfg, mel, init, iters, world, tile_frames=16, overlap=False, 
         for it in range(iters):
             for s in sessions:
                 s.iterate(it, 1 if overlap else 0)
-            ctx.sync()
+            # every session's boundary tiles (their own st_edge stream) must have finished before ANOTHER session's
+            # communication stream reads their partials: comm_begin only orders a session against its own tiles
+            for s in sessions:
+                s.sync()
             ptrs = [s.halo_ptrs(it) for s in sessions]
+            nbytes = HALO * sessions[0].halo_elem_bytes(it)
             for s in sessions:
                 s.comm_begin(it)
             for r in range(world - 1):      # boundary between rank r and r+1
-                ctx.check(ctx.lib.gomel_copy_d2d(ctx.h, ptrs[r + 1]["recv_tail"], ptrs[r]["send_tail"], HALO * 4,
+                ctx.check(ctx.lib.gomel_copy_d2d(ctx.h, ptrs[r + 1]["recv_tail"], ptrs[r]["send_tail"], nbytes,
                                                  sessions[r + 1].comm_stream))
-                ctx.check(ctx.lib.gomel_copy_d2d(ctx.h, ptrs[r]["recv_head"], ptrs[r + 1]["send_head"], HALO * 4,
+                ctx.check(ctx.lib.gomel_copy_d2d(ctx.h, ptrs[r]["recv_head"], ptrs[r + 1]["send_head"], nbytes,
                                                  sessions[r].comm_stream))
             for s in sessions:
                 s.comm_end(it)

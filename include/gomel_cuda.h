@@ -54,11 +54,14 @@ typedef struct {
                             registered tables for this (n_fft, n_mels). */
 } gomel_config;
 
-/* Precision of the Griffin-Lim loop (mel.ISTFT, mel/mel.go:76-139).  The loop is ill-conditioned in its FIRST
- * iterations only: a rounding error made in iteration 0-1 ends ~300x larger after 32 iterations, one made after
- * iteration ~8 does not grow (profiles/r02_gl_parity_sweep.md).  Default: the first `lead` iterations (4, see
- * gomel_set_lead_f64) run in float64 end to end (gl_f64.cuh), the rest in float32 -- within 1e-4 of the float64
- * reference for every start signal tried, where an all-float32 loop lands between 7e-6 and 3e-4.
+/* Precision of the Griffin-Lim loop (mel.ISTFT, mel/mel.go:76-139).  The loop is ill-conditioned: a rounding
+ * error made in iteration 0-1 ends ~300x larger after 32 iterations, one made in iteration 3 ~15x, and on flat
+ * spectra (white noise, silence) float32 errors keep growing in bursts over long runs, so an all-float32 loop lands
+ * between 7e-6 and 6e-4 of the float64 reference at 32 iterations and up to 5e-3 at 100
+ * (profiles/r02_gl_parity_sweep.md).  Default policy: the first `lead` iterations run in float64 end to end on
+ * the fused kernel of gl_f64.cuh, the rest in float32, with lead = max(4, GriffinLimIterations - 28) -- at least
+ * four float64 iterations, at most 28 float32 ones: <= 2e-5 of the reference on every (clip, start signal) of the
+ * sweep at 32 and at 100 iterations (tolerance 1e-4).  See gomel_set_lead_f64 / gomel_set_f32_tail.
  *   GOMEL_FLAG_F64      every iteration in float64 on the fused kernel (all from_mel entry points; the host-buffer
  *                       call then also reads the start signal and returns the waveform without a float32 step).
  *   GOMEL_FLAG_F64_REF  gomel_from_mel only: the round-1 strict path (one frame pair per CTA, spectra through HBM,
@@ -76,9 +79,11 @@ const char *gomel_version(void);
 unsigned long long gomel_launch_count(gomel_ctx *ctx);
 /* frames per tile for the tiled kernels; 0 = automatic (default) */
 int  gomel_set_tile_frames(gomel_ctx *ctx, int tile_frames);
-/* number of leading Griffin-Lim iterations run in float64 (default 4, env GOMEL_LEAD_F64; 0 = all float32 as in
- * round 1; values >= GriffinLimIterations behave like GOMEL_FLAG_F64).  Returns the previous value. */
+/* Griffin-Lim precision policy: lead = max(lead_iters, GriffinLimIterations - f32_tail) float64 iterations, then
+ * float32.  Defaults 4 and 28 (env GOMEL_LEAD_F64, GOMEL_F32_TAIL); lead_iters = 0 with f32_tail < 0 (unlimited)
+ * is the all-float32 loop of round 1.  Each returns the previous value (unlimited tail: INT_MAX). */
 int  gomel_set_lead_f64(gomel_ctx *ctx, int lead_iters);
+int  gomel_set_f32_tail(gomel_ctx *ctx, int f32_tail);
 
 /* ---- sizing: pad (mel/impl.go:429-455) + gossp NumFrames + ISTFT length (mel/mel.go:79) --- */
 int  gomel_frames(const gomel_config *cfg, long n_samples, long *n_padded, long *n_frames, long *ola_len);
@@ -196,6 +201,11 @@ int  gomel_ts_range(gomel_ts *ts, long *frame_begin, long *n_frames_local, long 
 int  gomel_ts_load(gomel_ts *ts, const float *d_mel_local, const float *d_init_local, unsigned long long seed);
 int  gomel_ts_iterate(gomel_ts *ts, int iter, int part);
 int  gomel_ts_halo_ptrs(gomel_ts *ts, int iter, float **send_tail, float **send_head, float **recv_tail, float **recv_head);
+/* The Griffin-Lim precision policy applies per iteration index: iterations [0, gomel_ts_lead_iters) run in float64
+ * (lead from the session's cfg.gl_iters; GOMEL_FLAG_F64: all) and exchange 2816 DOUBLES per partial -- the four
+ * pointers of gomel_ts_halo_ptrs then address float64 buffers; gomel_ts_halo_elem_bytes(iter) says which (8 / 4). */
+int  gomel_ts_halo_elem_bytes(gomel_ts *ts, int iter);
+int  gomel_ts_lead_iters(gomel_ts *ts);
 void *gomel_ts_comm_stream(gomel_ts *ts);                 /* cudaStream_t */
 int  gomel_ts_comm_begin(gomel_ts *ts, int iter);          /* comm stream waits for iteration iter's boundary tiles */
 int  gomel_ts_comm_end(gomel_ts *ts, int iter);            /* marks the exchange of iteration iter done */

@@ -285,6 +285,45 @@ def test_batch_from_mel_matches_single(mctx, lib, oracle):
         assert rel_l2(out[c], refs[c]) < TOL_GL
 
 
+def test_batch_headline_shape_against_float64(mctx, lib, oracle):
+    """The benchmarked call on the benchmarked shape: gomel_from_mel_batch_host, 64 clips x 10 s (342 frames),
+    Griffin-Lim 32, chunked pipeline (chunks of 24 -> ragged last chunk, three buffer sets in rotation), library
+    start signals from a seed AND injected start signals; a sample of clips is compared with the all-float64 fused
+    kernel on the same float32 inputs, one clip with the CPU oracle."""
+    from gomel_b200 import _lib
+    cfg = mel_cfg(lib, iters=32)
+    n_clips, frames, ola = 64, 342, 440576
+    base = [oracle.to_mel(oracle.config(), synth_clip(40 + c, 10.0)).astype(np.float32) for c in range(4)]
+    mel32 = np.stack([base[c % 4] for c in range(n_clips)])
+    rng = np.random.default_rng(9)
+    init32 = rng.random((n_clips, ola), dtype=np.float32)
+    out = np.empty((n_clips, ola), np.float32)
+    mctx.check(mctx.lib.gomel_from_mel_batch_host(
+        mctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), n_clips, frames,
+        init32.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_void_p), 24))
+    cfg64 = lib.make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=32, flags=_lib.FLAG_F64)
+    worst = 0.0
+    for c in (0, 1, 23, 24, 47, 48, 63):
+        exact = mctx.from_mel(cfg64, mel32[c].astype(np.float64), init=init32[c].astype(np.float64))
+        worst = max(worst, rel_l2(out[c], exact))
+        assert rel_l2(out[c], exact) < TOL_GL, (c, rel_l2(out[c], exact))
+    ref = oracle.from_mel(oracle.config(gl_iters=32), mel32[63].astype(np.float64), init32[63].astype(np.float64))
+    assert rel_l2(out[63], ref) < TOL_GL
+    # device-resident batch call on the same inputs: same kernels, same grouping rules -> same tolerance
+    d_mel, d_init, d_out = mctx.dev_malloc(mel32.nbytes), mctx.dev_malloc(init32.nbytes), mctx.dev_malloc(out.nbytes)
+    mctx.h2d(d_mel, mel32)
+    mctx.h2d(d_init, init32)
+    mctx.check(mctx.lib.gomel_from_mel_dev(mctx.h, C.byref(cfg), d_mel, n_clips, frames, d_init, 0, ola, d_out))
+    dev = np.empty_like(out)
+    mctx.d2h(dev, d_out)
+    for p in (d_mel, d_init, d_out):
+        mctx.dev_free(p)
+    for c in (0, 31, 32, 63):
+        exact = mctx.from_mel(cfg64, mel32[c].astype(np.float64), init=init32[c].astype(np.float64))
+        assert rel_l2(dev[c], exact) < TOL_GL, (c, rel_l2(dev[c], exact))
+    print(f"batch 64 x 10 s GL-32: worst sampled rel-L2 vs float64 {worst:.2e}")
+
+
 def test_batch_from_mel_pcm16_is_the_wav_quantisation_of_the_float_output(mctx, lib):
     """gomel_from_mel_batch_host_pcm16 == dumpwav's int16(clamp(v) * 32767) (mel/impl.go:195-232) of the float32 form"""
     cfg = mel_cfg(lib, iters=2)
@@ -348,10 +387,13 @@ def test_launch_counter_counts_kernels(mctx, lib, oracle):
 
 
 # ------------------------------------------------------------------ time-split (config 5) on one GPU
-@pytest.mark.parametrize("world,overlap,seconds,iters", [(2, False, 2.0, 3), (3, True, 2.0, 4), (4, True, 3.1, 2)])
+@pytest.mark.parametrize("world,overlap,seconds,iters", [(2, False, 2.0, 3), (3, True, 2.0, 4), (4, True, 3.1, 2),
+                                                         (2, True, 2.0, 7), (3, False, 2.6, 6), (4, True, 3.1, 9)])
 def test_timesplit_emulated_ranks_match_single_gpu(mctx, lib, oracle, world, overlap, seconds, iters):
     """world ranks emulated as sessions of one process: boundary partials exchanged by D2D copies.
-    With the same tile size the partial sums are identical -> bit-identical to the unsplit run."""
+    With the same tile size the partial sums are identical -> bit-identical to the unsplit run.  Iteration counts
+    <= 4 run entirely on the float64 kernel (2816 doubles per partial), larger ones cross the float64 -> float32
+    hand-over of the precision policy in the middle of the exchange protocol."""
     from gomel_b200 import timesplit
     cfg = mel_cfg(lib, iters=iters)
     wav = synth_clip(50, seconds)
@@ -365,17 +407,16 @@ def test_timesplit_emulated_ranks_match_single_gpu(mctx, lib, oracle, world, ove
     whole = mctx.from_mel(cfg, mel32, init=init.astype(np.float32).astype(np.float64))
     mctx.set_tile_frames(0)
     assert split.shape == (ola,)
-    assert np.array_equal(split.astype(np.float64), whole)
+    assert np.array_equal(split, whole.astype(np.float32))
     ref = oracle.from_mel(oracle.config(gl_iters=iters), mel, init.astype(np.float32).astype(np.float64))
     assert rel_l2(split, ref) < TOL_GL
 
 
-@pytest.mark.parametrize("world,tile,edge", [(2, 12, 4), (3, 10, 6), (2, 30, 8)])
-def test_timesplit_short_boundary_tiles(mctx, lib, oracle, world, tile, edge):
+@pytest.mark.parametrize("world,tile,edge,iters", [(2, 12, 4, 3), (3, 10, 6, 6), (2, 30, 8, 5)])
+def test_timesplit_short_boundary_tiles(mctx, lib, oracle, world, tile, edge, iters):
     """non-uniform tiling (short tiles next to a rank boundary, long interior tiles): same result as the unsplit
     run up to the order of the partial sums, and inside the Griffin-Lim tolerance of the oracle"""
     from gomel_b200 import timesplit
-    iters = 3
     cfg = mel_cfg(lib, iters=iters)
     mel = oracle.to_mel(oracle.config(), synth_clip(51, 3.3))
     frames = len(mel) // 192
@@ -456,7 +497,7 @@ def test_full_size_properties(mctx, lib, oracle):
     mel = m.ToMel(wav)
     assert mel.shape == (342 * 192, 2)
     assert rel_l2(np.exp(mel), np.exp(oracle.to_mel(oracle.config(), wav))) < TOL_STFT
-    init = np.random.default_rng(7).random(440576)      # a well-conditioned start signal (see the envelope test below)
+    init = np.random.default_rng(13).random(440576)     # a start signal an all-float32 loop misses the tolerance on (2e-4)
     m.InitSignal = init
     outs = []
     for tile in (0, 38, 342):
@@ -492,47 +533,104 @@ def _mel_obj(iters, strict):
     return m
 
 
+@pytest.mark.parametrize("strict", [True, "ref"])
 @pytest.mark.parametrize("seconds,iters,seed", [(0.3, 0, 1), (0.45, 3, 2), (1.5, 32, 5), (1.0, 100, 13)])
-def test_strict_f64_griffin_lim_matches_oracle(mctx, oracle, seconds, iters, seed):
-    """GOMEL_FLAG_F64: the whole loop in float64 -> 1e-10 of the reference for any start signal / iteration count"""
+def test_strict_f64_griffin_lim_matches_oracle(mctx, oracle, seconds, iters, seed, strict):
+    """GOMEL_FLAG_F64 (fused float64 kernel, gl_f64.cuh) and GOMEL_FLAG_F64_REF (round-1 strict path): the whole loop
+    in float64 -> 1e-10 of the reference for any start signal / iteration count"""
     wav = synth_clip(15, seconds)
     ocfg = oracle.config(gl_iters=iters)
     mel = oracle.to_mel(ocfg, wav)
     frames = len(mel) // 192
     init = np.random.default_rng(seed).random(4096 + (frames - 1) * 1280)
-    m = _mel_obj(iters, True)
+    m = _mel_obj(iters, strict)
     m.InitSignal = init
-    got = m.FromMel(mel.copy())
-    ref = oracle.from_mel(ocfg, mel, init)
-    assert got.shape == ref.shape
-    assert rel_l2(got, ref) < 1e-10, rel_l2(got, ref)
+    for tile in (0, 6):
+        mctx.set_tile_frames(tile)
+        got = m.FromMel(mel.copy())
+        mctx.set_tile_frames(0)
+        ref = oracle.from_mel(ocfg, mel, init)
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < 1e-10, (tile, rel_l2(got, ref))
 
 
-def test_fp32_deviation_is_the_algorithms_conditioning(mctx, oracle):
-    """10 s clip, 32 iterations, start signals for which float32 leaves the 1e-4 band (seed 13) and stays in it
-    (seed 7).  The strict float64 path is the reference here (checked against the oracle above and, at 1.5 s,
-    below 1e-10); it shows that (a) float64 reproduces itself, (b) merely rounding the START SIGNAL to float32
-    already moves the float64 result by the same order as the float32 pipeline's deviation: the gap is
-    Griffin-Lim's sensitivity, not a kernel defect."""
-    wav = synth_clip(0, 10.0)
+def test_fused_f64_matches_oracle_and_strict_path_full_size(mctx, oracle):
+    """10 s clip, 32 iterations (the bench shape): fused float64 kernel vs the CPU oracle (~10 s of CPU) and vs the
+    round-1 strict path; several tilings (different partial-sum orders at tile edges)"""
+    wav = synth_clip(3, 10.0)
     mel = oracle.to_mel(oracle.config(), wav)
-    for seed, must_pass in ((7, True), (13, False)):
-        init = np.random.default_rng(seed).random(440576)
-        ms = _mel_obj(32, True)
-        ms.InitSignal = init
-        exact = ms.FromMel(mel.copy())
-        ms.InitSignal = init.astype(np.float32).astype(np.float64)
-        perturbed = ms.FromMel(mel.copy())
-        mf = _mel_obj(32, False)
-        mf.InitSignal = init
-        fast = mf.FromMel(mel.copy())
-        sens = rel_l2(perturbed, exact)          # float64 arithmetic, start signal rounded to float32 (6e-8 relative)
-        dev = rel_l2(fast, exact)                # float32 pipeline (rounds every iteration)
-        print(f"seed {seed}: float64 sensitivity to a 6e-8 start perturbation {sens:.2e}; float32 pipeline deviation {dev:.2e}")
-        assert sens > 5e-7                       # amplification >= 10x of a single float32 rounding
-        assert dev < 200 * sens                  # 32 iterations x several roundings each, same amplification
-        if must_pass:
-            assert dev < TOL_GL
+    init = np.random.default_rng(5).random(440576)
+    ref = oracle.from_mel(oracle.config(gl_iters=32), mel, init)
+    m = _mel_obj(32, "ref")
+    m.InitSignal = init
+    assert rel_l2(m.FromMel(mel.copy()), ref) < 1e-10
+    m = _mel_obj(32, True)
+    m.InitSignal = init
+    for tile in (0, 18, 342):
+        mctx.set_tile_frames(tile)
+        got = m.FromMel(mel.copy())
+        mctx.set_tile_frames(0)
+        assert rel_l2(got, ref) < 1e-10, (tile, rel_l2(got, ref))
+
+
+def _sweep_clips():
+    kinds = [("clip%d" % c, synth_clip(c, 10.0)) for c in range(4)]
+    kinds.append(("white_noise", np.random.default_rng(77).uniform(-1, 1, 441000)))
+    kinds.append(("silence", np.zeros(441000)))
+    return kinds
+
+
+@pytest.mark.parametrize("iters", [32, 100])
+def test_gl_precision_policy_sweep(mctx, oracle, iters):
+    """The path bench.py measures (default precision policy: lead = max(4, iters - 28) float64 iterations, then
+    float32) against the all-float64 fused kernel (itself < 1e-10 of the oracle, tests above) on the bench shape:
+    4 synthetic clips + white noise + silence, 10 s each, 16 start signals each, at 32 and at 100 iterations.
+    EVERY pair must be inside the north-star tolerance -- no hand-picked seeds.  The all-float32 loop of round 1 is
+    run beside it and its pass fraction printed (it is below 1)."""
+    worst, worst32, n, n32_pass = 0.0, 0.0, 0, 0
+    for name, wav in _sweep_clips():
+        mel = oracle.to_mel(oracle.config(), wav)
+        for seed in range(100, 116):
+            init = np.random.default_rng(seed).random(440576)
+            m = _mel_obj(iters, True)
+            m.InitSignal = init
+            exact = m.FromMel(mel.copy())
+            m = _mel_obj(iters, False)
+            m.InitSignal = init
+            err = rel_l2(m.FromMel(mel.copy()), exact)
+            assert err < TOL_GL, (name, seed, iters, err)
+            worst = max(worst, err)
+            prev = mctx.set_gl_precision(0, -1)               # all float32
+            try:
+                e32 = rel_l2(m.FromMel(mel.copy()), exact)
+            finally:
+                mctx.set_gl_precision(*prev)
+            worst32 = max(worst32, e32)
+            n += 1
+            n32_pass += e32 < TOL_GL
+    print(f"GL-{iters}: {n} (clip, start signal) pairs; default policy max rel-L2 {worst:.2e} (all pass); "
+          f"all-float32 max {worst32:.2e}, pass fraction {n32_pass / n:.3f}")
+
+
+def test_gl_precision_knobs(mctx, oracle):
+    """gomel_set_lead_f64 / gomel_set_f32_tail: lead >= iters equals GOMEL_FLAG_F64 up to the final float32 narrowing;
+    zero-iteration and 1-iteration runs work in every mode"""
+    wav = synth_clip(4, 0.6)
+    mel = oracle.to_mel(oracle.config(), wav)
+    frames = len(mel) // 192
+    init = np.random.default_rng(3).random(4096 + (frames - 1) * 1280)
+    for iters in (0, 1, 2, 5, 6):
+        ref = oracle.from_mel(oracle.config(gl_iters=iters), mel, init)
+        for lead, tail in ((0, -1), (1, -1), (4, 28), (5, 0), (100, -1)):
+            prev = mctx.set_gl_precision(lead, tail)
+            try:
+                m = _mel_obj(iters, False)
+                m.InitSignal = init
+                got = m.FromMel(mel.copy())
+            finally:
+                mctx.set_gl_precision(*prev)
+            assert rel_l2(got, ref) < (1e-10 if lead >= iters else TOL_GL), (iters, lead, tail, rel_l2(got, ref))
+    assert mctx.set_gl_precision(4, 28) == (4, 28)
 
 
 # ------------------------------------------------------------------ small / unusual inputs of the buffer API

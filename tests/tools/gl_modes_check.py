@@ -35,12 +35,12 @@ def mel_obj(iters, strict=False):
 
 def run(mel, init, iters, strict=False, lead=None):
     ctx = _lib.default_context(0)
-    prev = ctx.set_lead_f64(lead) if lead is not None else None
+    prev = ctx.set_gl_precision(lead, -1) if lead is not None else None     # exactly `lead` float64 iterations
     m = mel_obj(iters, strict)
     m.InitSignal = init
     out = m.FromMel(mel.copy())
     if prev is not None:
-        ctx.set_lead_f64(prev)
+        ctx.set_gl_precision(*prev)
     return out
 
 
@@ -107,7 +107,7 @@ def speed(clips=256):
                                      ("f32_32it", 32, 0, 0)):
         c = _lib.make_config(gl_iters=iters, flags=flags)
         if lead is not None:
-            ctx.set_lead_f64(lead)
+            ctx.set_gl_precision(lead, -1)
         for rep in range(3):
             ctx.timer_start()
             ctx.check(ctx.lib.gomel_from_mel_dev(ctx.h, C.byref(c), d_mel, clips, frames, None, 7, ola, d_out))
@@ -120,7 +120,7 @@ def speed(clips=256):
                      "f32_frame_iter_per_s": fi * hn / (hms / 1e3) if hn else None,
                      "audio_s_per_s": clips * frames * 1280 / 44100 / (ms / 1e3)}
         print(name, json.dumps(res[name]), flush=True)
-    ctx.set_lead_f64(4)
+    ctx.set_gl_precision(4, 28)
     json.dump(res, open(os.path.join(OUT, f"gl_modes_speed_{clips}.json"), "w"), indent=1)
 
 
