@@ -38,6 +38,7 @@ CLIP_SECONDS = 10.0
 CLIPS_PER_GPU = 1024
 BASE_CLIPS = 32                      # distinct spectrograms, tiled to CLIPS_PER_GPU
 BYTES_PER_FRAME_ITER = 18436         # 2049*4 magnitudes + 1280*4 read + 1280*4 write
+BYTES_PER_FRAME_ITER_F64 = 36872     # the float64 lead iterations move the same items as doubles
 BYTES_PER_FRAME_ONCE = 9732          # K3: read mel 1536 + write magnitudes 8196
 METRIC = "mel2wav_griffinlim32_audio_seconds_per_second"
 UNIT = "audio-s/s"
@@ -103,6 +104,20 @@ class ClockSampler:
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def bind_cpu_share(local_rank, local_world):
+    """No NUMA information: give every local rank its own contiguous share of the allowed CPUs, so the ranks' copy
+    threads and first-touch pinned pages do not migrate over each other."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(local_world, 1)
+        if per >= 1 and local_world > 1:
+            os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
+            return [cpus[local_rank * per], cpus[(local_rank + 1) * per - 1]]
+    except Exception:
+        pass
+    return None
 
 
 def bind_to_gpu_numa(local_rank):
@@ -191,6 +206,167 @@ def workload_config(n_gpus):
 
 
 # ------------------------------------------------------------------------------- product arm
+def host_link_probe(local_rank, use_dist, mb=512, reps=4):
+    """Ceiling of the end-to-end path: pinned H2D and D2H copies running concurrently on this GPU -- and, under
+    torchrun, on every rank's GPU at the same time (barrier before, max time over ranks).  torch is plumbing here."""
+    import torch
+    dev = torch.device("cuda", local_rank)
+    n = mb << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def one():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    one()
+    torch.cuda.synchronize(dev)
+    if use_dist:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    world = 1
+    if use_dist:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+        world = dist.get_world_size()
+    per_dir = n * reps / dt / 1e9
+    del h_in, h_out, d_in, d_out
+    torch.cuda.empty_cache()
+    return {"what": f"concurrent pinned H2D + D2H of {mb} MiB per direction per GPU, all {world} GPU(s) at once, max over ranks",
+            "gbs_per_direction_per_gpu": per_dir, "aggregate_gbs_both_directions": 2 * per_dir * world}
+
+
+def timesplit_measure(ctx, cfg, rank, local_rank, world, use_dist, seconds, steps, warmup, ts_tile=0, ts_edge=8,
+                      overlap=True, exchange_kind="native"):
+    """configs[4]: ONE long clip, Griffin-Lim 32 it, frames split by time across the ranks, two 2816-element
+    partials exchanged per boundary per iteration over NCCL.  A step = the whole FromMel of the clip: target
+    magnitudes + start signal (gomel_ts_load from device-resident mel), 32 iterations under the precision policy
+    (float64 lead iterations exchange doubles), timed with the host clock around a stream-synchronised region,
+    max over ranks."""
+    from gomel_b200 import _lib, timesplit
+    from util import synth_clip
+    if use_dist:
+        import torch
+        import torch.distributed as dist
+    n_total = int(round(seconds * SR))
+    _, frames_total, ola = _lib.frames(cfg, n_total)
+    # spectrogram: a 60 s synthetic clip's mel (GPU ToMel) repeated along time
+    base_n = 60 * SR
+    wav = synth_clip(9000, 60.0).astype(np.float32)[None, :]
+    _, base_frames, _ = _lib.frames(cfg, base_n)
+    base_mel = np.empty((1, base_frames * N_MELS * 2), np.float32)
+    ctx.check(ctx.lib.gomel_to_mel_batch_host(ctx.h, C.byref(cfg), wav.ctypes.data_as(C.c_void_p), 1, base_n,
+                                              base_mel.ctypes.data_as(C.c_void_p), 1))
+    base_mel = base_mel.reshape(base_frames, N_MELS * 2)
+    if ts_tile <= 0:
+        # frames per interior tile: fill whole waves of 2 CTAs/SM (296 CTAs) with this rank's tiles; long tiles
+        # amortise the per-tile prologue, the short boundary tiles (ts_edge) keep the exchange path short
+        per_rank = (frames_total + world - 1) // world
+        best = (0.0, 16)
+        for T in range(16, 122, 2):
+            tiles = (per_rank + T - 1) // T
+            eff = tiles / (((tiles + 295) // 296) * 296.0) + 0.0005 * T
+            if eff > best[0]:
+                best = (eff, T)
+        ts_tile = best[1]
+    s = timesplit.Session(ctx, cfg, frames_total, rank, world, ts_tile, ts_edge)
+    idx = (np.arange(s.frame_begin, s.frame_begin + s.n_frames) % base_frames)
+    mel_local = np.ascontiguousarray(base_mel[idx].reshape(-1, 2))
+    d_mel = ctx.dev_malloc(mel_local.nbytes)
+    ctx.h2d(d_mel, mel_local)
+    exchange = timesplit.NcclExchange(s) if (use_dist and exchange_kind != "native") else (lambda it: None)
+    native = timesplit.NativeNccl(s) if exchange_kind == "native" else None
+
+    def barrier():
+        s.sync()
+        if use_dist:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def one_step(k):
+        s.load_dev(d_mel, None, seed=9001 + k)
+        if native is not None:
+            native.run(0, GL_ITERS, overlap=overlap)
+            return
+        for it in range(GL_ITERS):
+            if overlap:
+                s.iterate(it, 1); exchange(it); s.iterate(it, 2)
+            else:
+                s.iterate(it, 0); exchange(it)
+
+    for k in range(warmup):
+        one_step(k)
+    barrier()
+    launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one_step(100 + k)
+    s.sync()
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    launches = ctx.launch_count() - launches0
+    if use_dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    lead = s.lead_iters()
+    s.close()
+    ctx.dev_free(d_mel)
+    audio_s = frames_total * HOP / SR
+    peak, _ = peaks()
+    fi = frames_total * GL_ITERS * steps / (ms / 1e3)
+    bytes_iter = (min(lead, GL_ITERS) * BYTES_PER_FRAME_ITER_F64 + max(GL_ITERS - lead, 0) * BYTES_PER_FRAME_ITER) / GL_ITERS
+    return {
+        "workload": "timesplit", "metric": METRIC, "value": audio_s * steps / (ms / 1e3), "unit": UNIT,
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "ms_per_iteration": ms / steps / GL_ITERS, "higher_is_better": True, "scaling": "strong",
+        "dtype": f"f64 x{min(lead, GL_ITERS)} + f32 x{max(GL_ITERS - lead, 0)} iterations", "data": "synthetic",
+        "config": {"workload": f"configs[4]: one {seconds:.0f} s 44.1 kHz clip ({frames_total} frames), Griffin-Lim "
+                               f"{GL_ITERS} it, frames split by time over {world} GPU(s), NCCL exchange of two 2816-element "
+                               f"partials per boundary per iteration ({exchange_kind} NCCL), tile {ts_tile} frames, boundary tiles {ts_edge}, overlap={bool(overlap)}",
+                   "step": "mel -> magnitudes + start signal + all iterations (whole FromMel of the clip)",
+                   "timing": "host wall clock around stream-synchronised region, max over ranks"},
+        "frame_iterations_per_s": fi, "hbm_frac_whole_job": fi * bytes_iter / 1e9 / (peak * world),
+        "gpu_launches": int(launches)}
+
+
+def parity_record(ctx, cfg, _lib, base_mel, frames, ola, n=4):
+    """rel-L2 of n bench clips through the benchmarked call (gomel_from_mel_batch_host, default precision policy,
+    injected start signals) against the all-float64 fused kernel on the same inputs -- the number the north-star
+    tolerance (1e-4) is about; the full sweep is tests/test_gpu_parity.py::test_gl_precision_policy_sweep."""
+    nb = min(n, len(base_mel))
+    mel32 = np.ascontiguousarray(base_mel[:nb])
+    init32 = np.random.default_rng(4242).random((nb, ola), dtype=np.float32)
+    out = np.empty((nb, ola), np.float32)
+    ctx.check(ctx.lib.gomel_from_mel_batch_host(ctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), nb, frames,
+                                                init32.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_void_p), nb))
+    cfg64 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS, flags=_lib.FLAG_F64)
+    prev = ctx.set_gl_precision(0, -1)
+    out32 = np.empty((nb, ola), np.float32)
+    try:
+        ctx.check(ctx.lib.gomel_from_mel_batch_host(ctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), nb, frames,
+                                                    init32.ctypes.data_as(C.c_void_p), 0, out32.ctypes.data_as(C.c_void_p), nb))
+    finally:
+        ctx.set_gl_precision(*prev)
+    errs, errs32 = [], []
+    for c in range(nb):
+        exact = ctx.from_mel(cfg64, mel32[c].reshape(-1, 2).astype(np.float64), init=init32[c].astype(np.float64))
+        d = np.linalg.norm(exact)
+        errs.append(float(np.linalg.norm(out[c] - exact) / d))
+        errs32.append(float(np.linalg.norm(out32[c] - exact) / d))
+    return {"what": f"{nb} bench clips, benchmarked call vs all-float64 fused kernel (GOMEL_FLAG_F64), same float32 inputs",
+            "rel_l2": errs, "rel_l2_max": max(errs), "tolerance": 1e-4, "all_float32_rel_l2": errs32,
+            "sweep": "profiles/r02_gl_parity_sweep.md (96 + 96 pairs, all inside 1e-4 under the default policy)"}
+
+
 def run_product(args):
     rank, local_rank, world = dist_env()
     n_gpus = world                      # one process per GPU; --gpus is informational when launched by torchrun
@@ -204,6 +380,7 @@ def run_product(args):
     from util import synth_clip
 
     numa_node = bind_to_gpu_numa(local_rank) if args.numa else None
+    cpu_share = bind_cpu_share(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if (args.numa and numa_node is None) else None
     ctx = _lib.Context(local_rank)
     cfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
     ctx.set_mel_tables(cfg, 0.0, 16000.0)
@@ -234,8 +411,15 @@ def run_product(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    def step_device(seed):
-        ctx.check(ctx.lib.gomel_from_mel_dev(ctx.h, C.byref(cfg), d_mel, clips, frames, None, seed, ola, d_out))
+    def reduce_max(vals):
+        if not use_dist:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def step_device(seed, n_clips=clips, c=cfg):
+        ctx.check(ctx.lib.gomel_from_mel_dev(ctx.h, C.byref(c), d_mel, n_clips, frames, None, seed, ola, d_out))
 
     def step_e2e(seed):
         ctx.check(ctx.lib.gomel_from_mel_batch_host(ctx.h, C.byref(cfg), h_mel.ctypes.data_as(C.c_void_p), clips, frames,
@@ -249,7 +433,7 @@ def run_product(args):
     sampler.start()
     time.sleep(0.25)
     launches0 = ctx.launch_count()
-    hot_ms, hot_n = 0.0, 0
+    hot_ms, hot_n, lead_ms, lead_n = 0.0, 0, 0.0, 0
     t_wall0 = time.time()
     ctx.timer_start()
     for s in range(args.steps):
@@ -258,6 +442,9 @@ def run_product(args):
             ms, nl = ctx.last_hot_kernel_ms()     # waits for this step's last Griffin-Lim launch
             hot_ms += ms
             hot_n += nl
+            ms, nl = ctx.last_lead_kernel_ms()
+            lead_ms += ms
+            lead_n += nl
     dev_ms = ctx.timer_stop()
     barrier()
     t_wall1 = time.time()
@@ -293,10 +480,68 @@ def run_product(args):
     pcm_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
-    if use_dist:
-        t = torch.tensor([dev_ms, e2e_ms, pcm_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, pcm_ms = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_ms, pcm_ms = reduce_max([dev_ms, e2e_ms, pcm_ms])
+
+    # ---- the other two precision modes on the same batch, device-resident (one timed step each after one warm-up)
+    modes = {}
+    cfg_f64 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS, flags=_lib.FLAG_F64)
+    for name, c, prec in (("all_float32", cfg, (0, -1)), ("all_float64", cfg_f64, None)):
+        prev = ctx.set_gl_precision(*prec) if prec else None
+        step_device(1, c=c)
+        barrier()
+        ctx.timer_start()
+        step_device(2, c=c)
+        ms = ctx.timer_stop()
+        if prev:
+            ctx.set_gl_precision(*prev)
+        barrier()
+        ms = reduce_max([ms])[0]
+        modes[name] = {"ms_per_step": ms, "value": world * clips * frames * HOP / SR / (ms / 1e3)}
+
+    # ---- strong scaling of configs[3]: 1024 clips in TOTAL, 1024 / N per rank (device-resident and end to end)
+    strong = None
+    if args.strong:
+        sc = max(1, CLIPS_PER_GPU // world)
+        if sc <= clips:
+            for w in range(2):
+                step_device(w, n_clips=sc)
+            barrier()
+            ctx.timer_start()
+            for s in range(args.steps):
+                step_device(4000 + s, n_clips=sc)
+            s_ms = ctx.timer_stop()
+            barrier()
+            call = lambda sd: ctx.check(ctx.lib.gomel_from_mel_batch_host(
+                ctx.h, C.byref(cfg), h_mel.ctypes.data_as(C.c_void_p), sc, frames, None, sd, h_out.ctypes.data_as(C.c_void_p),
+                min(args.chunk, max(64, sc // 2))))
+            call(0)
+            barrier()
+            t0 = time.perf_counter()
+            for s in range(args.steps):
+                call(5000 + s)
+            ctx.sync()
+            se_ms = (time.perf_counter() - t0) * 1e3
+            barrier()
+            s_ms, se_ms = reduce_max([s_ms, se_ms])
+            tot = sc * world * frames * HOP / SR
+            strong = {"workload": f"configs[3] strong scaling: {sc * world} clips in total, {sc} per GPU", "scaling": "strong",
+                      "clips_per_gpu": sc, "value": tot * args.steps / (s_ms / 1e3), "ms_per_step": s_ms / args.steps,
+                      "frame_iterations_per_s": sc * world * frames * GL_ITERS * args.steps / (s_ms / 1e3),
+                      "e2e_value": tot * args.steps / (se_ms / 1e3), "e2e_ms_per_step": se_ms / args.steps, "unit": UNIT}
+
+    # ---- ceiling of the end-to-end path: what the host link moves with every GPU copying at once
+    link = None
+    if args.link:
+        try:
+            link = host_link_probe(local_rank, use_dist)
+        except Exception as e:       # noqa: BLE001  (diagnostic leg only)
+            link = {"unavailable": repr(e)[:200]}
+
+    # ---- configs[4]: one long clip split by time over the ranks (NCCL halo exchange), same process group
+    ts = None
+    if args.timesplit_seconds > 0:
+        ts = timesplit_measure(ctx, cfg, rank, local_rank, world, use_dist, args.timesplit_seconds, max(1, min(args.steps, 3)), 1,
+                               args.ts_tile, args.ts_edge, args.ts_overlap, args.ts_exchange)
 
     audio_s_per_step = world * clips * frames * HOP / SR          # seconds of audio covered by the frames
     value = audio_s_per_step * args.steps / (dev_ms / 1e3)
@@ -325,7 +570,16 @@ def run_product(args):
                         "kernel_share_of_step": hot_ms / dev_ms,
                         "launch_note": "one timed launch = one Griffin-Lim iteration over the whole batch, issued as two "
                                        "concurrent half-batch launches of the kernel (clips split over two streams)",
-                        "frame_iterations_per_s_per_gpu": frame_iters * args.steps / (hot_ms / 1e3)}
+                        "frame_iterations_per_s_per_gpu": clips * frames * hot_n / (hot_ms / 1e3)}
+            if lead_n:
+                l_s = lead_ms / 1e3 / lead_n
+                l_ach = BYTES_PER_FRAME_ITER_F64 * clips * frames / l_s / 1e9
+                roofline["lead_kernel"] = {
+                    "kernel": "k_gl_iter_f64<5>", "bound": "hbm nominally; FP64 pipe + shared memory in practice",
+                    "achieved": l_ach, "peak": peak, "unit": "GB/s", "frac": l_ach / peak,
+                    "algorithmic_bytes_per_launch": BYTES_PER_FRAME_ITER_F64 * clips * frames, "avg_launch_ms": l_s * 1e3,
+                    "launches_timed": lead_n, "kernel_share_of_step": lead_ms / dev_ms,
+                    "frame_iterations_per_s_per_gpu": clips * frames * lead_n / (lead_ms / 1e3)}
         cpu = None
         if world == 1:                              # rank 0 at N=1 only
             if not args.no_cpu:
@@ -335,22 +589,36 @@ def run_product(args):
                 cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                        "sample": f"{cores} clips x {secs:.0f} s ({fr} frames), GL-{GL_ITERS}, one clip per host thread, "
                                  f"{step_s:.1f} s wall; float64 C port of the Go path (no Go toolchain in the image)"}
+        lead_it = lead_n // max(args.steps, 1) if args.per_kernel else None
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_mel.nbytes),
+               "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": e2e_ms / args.steps,
+               "api": "gomel_from_mel_batch_host (pinned host float32 in/out, H2D / magnitudes / iterations / D2H on four streams, three chunk buffer sets)",
+               "host_numa_node": numa_node, "cpu_share": cpu_share,
+               "checksum": checksum,
+               "pcm16": {"value": audio_s_per_step * args.steps / (pcm_ms / 1e3), "ms_per_step": pcm_ms / args.steps,
+                         "d2h_bytes_per_step": int(h_pcm.nbytes),
+                         "api": "gomel_from_mel_batch_host_pcm16 (int16 PCM out, the sample format of cmd/towav)"}}
+        if link and "gbs_per_direction_per_gpu" in link:
+            bw = link["gbs_per_direction_per_gpu"] * 1e9
+            floor_ms = max(h_mel.nbytes, h_out.nbytes) / bw * 1e3
+            e2e["link_floor_ms_per_step"] = floor_ms
+            e2e["frac_of_link_ceiling"] = floor_ms / (e2e_ms / args.steps)
+            e2e["compute_floor_ms_per_step"] = dev_ms / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_gpus),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_mel.nbytes),
-                    "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": e2e_ms / args.steps,
-                    "api": "gomel_from_mel_batch_host (pinned host float32 in/out, 3-stream pipeline)",
-                    "host_numa_node": numa_node,
-                    "checksum": checksum,
-                    "pcm16": {"value": audio_s_per_step * args.steps / (pcm_ms / 1e3), "ms_per_step": pcm_ms / args.steps,
-                              "d2h_bytes_per_step": int(h_pcm.nbytes),
-                              "api": "gomel_from_mel_batch_host_pcm16 (int16 PCM out, the sample format of cmd/towav)"}},
+            "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic", "config": workload_config(n_gpus),
+            "precision": {"policy": "lead = max(4, iters - 28) Griffin-Lim iterations in float64 (k_gl_iter_f64), the rest in float32 (k_gl_iter)",
+                          "float64_iterations": lead_it, "float32_iterations": (GL_ITERS - lead_it) if lead_it is not None else None,
+                          "other_modes_device_resident": modes},
+            "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "host_link": link, "strong_1024": strong, "timesplit": ts,
             "stft_frames_per_s": frame_iters * world * args.steps / (dev_ms / 1e3),
             "stft_frames_per_s_note": "Griffin-Lim frame-iterations (one analysis STFT + one synthesis ISTFT each) per second, whole job",
         }
+        if args.parity:
+            line["parity"] = parity_record(ctx, cfg, _lib, base_mel, frames, ola)
     if args.stft and rank == 0 and line is not None:
         line["stft_side"] = bench_to_mel(ctx, cfg, _lib, args)
         # configs[3] also names 100 iterations: same batch, same call, GriffinLimIterations = 100
@@ -362,24 +630,22 @@ def run_product(args):
         call(2)
         ms100 = ctx.timer_stop()
         line["cufft_comparison"] = bench_cufft_comparison(clips, frames)
-        # strict float64 path (parity instrument): one 10 s clip through the host-buffer API, 32 iterations
-        cfg64 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS, flags=_lib.FLAG_F64)
+        # the drop-in single-clip call (configs[0] shape: one clip, host float64 buffers): 2 and 32 iterations
         mel1 = base_mel[0].reshape(-1, 2).astype(np.float64)
         init1 = np.random.default_rng(1).random(ola)
-        ctx.from_mel(cfg64, mel1, init=init1)
-        t0 = time.perf_counter()
-        ctx.from_mel(cfg64, mel1, init=init1)
-        s64 = time.perf_counter() - t0
-        cfg32 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
-        ctx.from_mel(cfg32, mel1, init=init1)
-        t0 = time.perf_counter()
-        ctx.from_mel(cfg32, mel1, init=init1)
-        s32 = time.perf_counter() - t0
-        line["single_clip_host_api"] = {"workload": "gomel_from_mel, one 10 s clip, 32 iterations, float64 host buffers, incl. copies",
-                                        "float32_ms": s32 * 1e3, "strict_float64_ms": s64 * 1e3,
-                                        "float32_audio_s_per_s": frames * HOP / SR / s32,
-                                        "strict_float64_audio_s_per_s": frames * HOP / SR / s64}
-        line["gl100"] = {"workload": f"configs[3] with 100 iterations, {clips} clips, device-resident", "ms_per_step": ms100,
+        single = {"workload": "gomel_from_mel, one 10 s clip, float64 host buffers, incl. copies (the call mel.FromMel / cmd/towav makes)"}
+        for name, it_, fl in (("gl2", 2, 0), ("gl32", GL_ITERS, 0), ("gl32_all_float64", GL_ITERS, _lib.FLAG_F64)):
+            c1 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=it_, flags=fl)
+            for _ in range(3):
+                ctx.from_mel(c1, mel1, init=init1)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ctx.from_mel(c1, mel1, init=init1)
+            sec = (time.perf_counter() - t0) / 5
+            single[name] = {"ms": sec * 1e3, "audio_s_per_s": frames * HOP / SR / sec}
+        line["single_clip_host_api"] = single
+        line["gl100"] = {"workload": f"configs[3] with 100 iterations (72 float64 + 28 float32 under the policy), {clips} clips, device-resident",
+                         "ms_per_step": ms100,
                          "audio_s_per_s": clips * frames * HOP / SR / (ms100 / 1e3),
                          "frame_iterations_per_s": clips * frames * 100 / (ms100 / 1e3)}
     ctx.dev_free(d_mel)
@@ -398,9 +664,7 @@ def run_product(args):
 
 # ------------------------------------------------------------------------------- config 5 side bench
 def run_timesplit(args):
-    """configs[4]: ONE 1-hour 44.1 kHz clip, Griffin-Lim 32 it, frames split by time across the
-    ranks, two 2816-float partials exchanged per boundary per iteration over NCCL (side measurement,
-    printed as its own JSON line with "workload": "timesplit")."""
+    """configs[4] on its own (`--workload timesplit`): prints the time-split record as its own JSON line."""
     rank, local_rank, world = dist_env()
     use_dist = world > 1
     if use_dist:
@@ -408,88 +672,14 @@ def run_timesplit(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from gomel_b200 import _lib, timesplit
-    from util import synth_clip
+    from gomel_b200 import _lib
     ctx = _lib.Context(local_rank)
     cfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS)
     ctx.set_mel_tables(cfg, 0.0, 16000.0)
-    n_total = int(round(args.seconds * SR))
-    _, frames_total, ola = _lib.frames(cfg, n_total)
-    # spectrogram: a 60 s synthetic clip's mel (GPU ToMel) repeated along time
-    base_n = 60 * SR
-    wav = synth_clip(9000, 60.0).astype(np.float32)[None, :]
-    _, base_frames, _ = _lib.frames(cfg, base_n)
-    base_mel = np.empty((1, base_frames * N_MELS * 2), np.float32)
-    ctx.check(ctx.lib.gomel_to_mel_batch_host(ctx.h, C.byref(cfg), wav.ctypes.data_as(C.c_void_p), 1, base_n,
-                                              base_mel.ctypes.data_as(C.c_void_p), 1))
-    base_mel = base_mel.reshape(base_frames, N_MELS * 2)
-    if args.ts_tile <= 0:
-        # frames per interior tile: fill whole waves of 2 CTAs/SM (296 CTAs) with this rank's tiles; long tiles
-        # amortise the per-tile prologue, the short boundary tiles (--ts-edge) keep the exchange path short
-        per_rank = (frames_total + world - 1) // world
-        best = (0.0, 16)
-        for T in range(16, 122, 2):
-            tiles = (per_rank + T - 1) // T
-            eff = tiles / (((tiles + 295) // 296) * 296.0) + 0.0005 * T
-            if eff > best[0]:
-                best = (eff, T)
-        args.ts_tile = best[1]
-    s = timesplit.Session(ctx, cfg, frames_total, rank, world, args.ts_tile, args.ts_edge)
-    idx = (np.arange(s.frame_begin, s.frame_begin + s.n_frames) % base_frames)
-    s.load(base_mel[idx].reshape(-1, 2), None, seed=9001)
-    exchange = timesplit.NcclExchange(s) if use_dist else (lambda it: None)
-    native = timesplit.NativeNccl(s) if (args.ts_exchange == "native") else None
-
-    def barrier():
-        s.sync()
-        if use_dist:
-            torch.cuda.synchronize()
-            dist.barrier()
-
-    def one_step(it):
-        if native is not None:
-            native.run(it, GL_ITERS, overlap=args.ts_overlap)
-            return it + GL_ITERS
-        for _ in range(GL_ITERS):
-            if args.ts_overlap:
-                s.iterate(it, 1); exchange(it); s.iterate(it, 2)
-            else:
-                s.iterate(it, 0); exchange(it)
-            it += 1
-        return it
-
-    it = 0
-    for _ in range(args.warmup):
-        it = one_step(it)
-    barrier()
-    launches0 = ctx.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        it = one_step(it)
-    s.sync()
-    ms = (time.perf_counter() - t0) * 1e3
-    barrier()
-    launches = ctx.launch_count() - launches0
-    if use_dist:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-    s.close()
+    rec = timesplit_measure(ctx, cfg, rank, local_rank, world, use_dist, args.seconds, args.steps, args.warmup,
+                            args.ts_tile, args.ts_edge, args.ts_overlap, args.ts_exchange)
     if rank == 0:
-        audio_s = frames_total * HOP / SR
-        peak, peak_src = peaks()
-        fi = frames_total * GL_ITERS * args.steps / (ms / 1e3)
-        print(json.dumps({
-            "workload": "timesplit", "metric": METRIC, "value": audio_s * args.steps / (ms / 1e3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "ms_per_iteration": ms / args.steps / GL_ITERS, "higher_is_better": True, "scaling": "strong",
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[4]: one {args.seconds:.0f} s 44.1 kHz clip ({frames_total} frames), Griffin-Lim "
-                                   f"{GL_ITERS} it, frames split by time over {world} GPU(s), NCCL exchange of two 2816-float "
-                                   f"partials per boundary per iteration ({args.ts_exchange} NCCL), tile {args.ts_tile} frames, boundary tiles {args.ts_edge}, overlap={bool(args.ts_overlap)}",
-                       "timing": "host wall clock around stream-synchronised region, max over ranks"},
-            "frame_iterations_per_s": fi, "hbm_frac_whole_job": fi * BYTES_PER_FRAME_ITER / 1e9 / (peak * world),
-            "gpu_launches": int(launches)}))
+        print(json.dumps(rec))
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -625,6 +815,11 @@ def main():
     ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")
     ap.add_argument("--no-numa", dest="numa", action="store_false", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--tile", type=int, default=0, help="frames per tile (0 = library heuristic)")
+    ap.add_argument("--no-strong", dest="strong", action="store_false", help="skip the 1024-clips-in-total strong-scaling leg")
+    ap.add_argument("--no-link", dest="link", action="store_false", help="skip the host-link ceiling probe")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the parity sub-record")
+    ap.add_argument("--timesplit-seconds", type=float, default=3600.0,
+                    help="length of the single clip of the configs[4] sub-record (0 = skip)")
     ap.add_argument("--workload", default="clips", choices=["clips", "timesplit"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="timesplit: clip length")
     ap.add_argument("--ts-tile", type=int, default=0, help="timesplit: frames per tile (0 = fill whole waves)")

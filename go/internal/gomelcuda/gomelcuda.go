@@ -24,12 +24,23 @@ type Config struct {
 	NFFT, Hop, NMels, NFreqs, GLIters int
 	TuneMul, TuneAdd, VolumeBoost     float64
 	MelFmin, MelFmax                  float64 // key of the filterbank tables (with NFFT, NMels)
+	Flags                             int     // FlagF64: every Griffin-Lim iteration in float64 (GOMEL_FLAG_F64)
 }
+
+const (
+	FlagF64    = 1 // GOMEL_FLAG_F64
+	FlagF64Ref = 2 // GOMEL_FLAG_F64_REF (test instrument)
+)
+
+// oneZero stands in for an empty input: the reference's pad() grows an empty buffer to 15*Window-1 zeros
+// (mel/impl.go:429-455) and one zero sample pads to exactly the same signal, while &wav[0] of an empty slice
+// would panic before the cgo call.
+var oneZero = []float64{0}
 
 func (c Config) c() C.gomel_config {
 	return C.gomel_config{n_fft: C.int(c.NFFT), hop: C.int(c.Hop), n_mels: C.int(c.NMels), n_freqs: C.int(c.NFreqs),
 		gl_iters: C.int(c.GLIters), tune_mul: C.double(c.TuneMul), tune_add: C.double(c.TuneAdd),
-		volume_boost: C.double(c.VolumeBoost), mel_fmin: C.double(c.MelFmin), mel_fmax: C.double(c.MelFmax)}
+		volume_boost: C.double(c.VolumeBoost), flags: C.int(c.Flags), mel_fmin: C.double(c.MelFmin), mel_fmax: C.double(c.MelFmax)}
 }
 
 // Ctx owns one gomel_ctx.  Methods are safe for concurrent use: the library serialises calls per context
@@ -140,6 +151,9 @@ func (x *Ctx) setMelTables(cfg Config, fmin, fmax float64, force bool) error {
 
 // ToMel: [][2]float64 is a contiguous double[2n], passed as &out[0] (no Go pointer to Go pointer).
 func (x *Ctx) ToMel(cfg Config, wav []float64) ([][2]float64, error) {
+	if len(wav) == 0 {
+		wav = oneZero
+	}
 	_, frames, _, err := Frames(cfg, len(wav))
 	if err != nil {
 		return nil, err
@@ -184,6 +198,9 @@ func (x *Ctx) FromMel(cfg Config, mel [][2]float64, init []float64) ([]float64, 
 }
 
 func (x *Ctx) ToPhase(cfg Config, wav []float64) ([][2]float64, error) {
+	if len(wav) == 0 {
+		wav = oneZero
+	}
 	_, frames, _, err := Frames(cfg, len(wav))
 	if err != nil {
 		return nil, err
@@ -205,6 +222,13 @@ func (x *Ctx) FromPhase(cfg Config, spec [][2]float64) ([]float64, error) {
 	rc := C.gomel_from_phase(x.h, &cc, (*C.double)(unsafe.Pointer(&spec[0])), C.long(frames),
 		(*C.double)(unsafe.Pointer(&out[0])))
 	return out, x.err(rc)
+}
+
+// SetGLPrecision: at least `lead` float64 Griffin-Lim iterations first, at most `tail` float32 ones at the end
+// (tail < 0: unlimited).  Library defaults 4 and 28; (0, -1) is the all-float32 loop.
+func (x *Ctx) SetGLPrecision(lead, tail int) {
+	C.gomel_set_lead_f64(x.h, C.int(lead))
+	C.gomel_set_f32_tail(x.h, C.int(tail))
 }
 
 func (x *Ctx) Image(buf [][2]float64, mels int) ([]uint16, error) {

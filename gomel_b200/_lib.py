@@ -271,6 +271,8 @@ class Context:
     # ---- host-buffer API -------------------------------------------------------------
     def to_mel(self, cfg, wav):
         wav = np.ascontiguousarray(wav, np.float64)
+        if len(wav) == 0:            # the reference's pad() grows an empty buffer to 15*Window-1 zeros; one zero pads the same
+            wav = np.zeros(1)
         _, fr, _ = frames(cfg, len(wav))
         out = np.empty((fr * cfg.n_mels, 2), np.float64)
         self._mel_call(cfg, lambda: self.lib.gomel_to_mel(self.h, C.byref(cfg), wav.ctypes.data_as(_dp), len(wav),
@@ -297,6 +299,8 @@ class Context:
 
     def to_phase(self, cfg, wav):
         wav = np.ascontiguousarray(wav, np.float64)
+        if len(wav) == 0:
+            wav = np.zeros(1)
         _, fr, _ = frames(cfg, len(wav))
         out = np.empty((fr * cfg.n_freqs, 2), np.float64)
         self.check(self.lib.gomel_to_phase(self.h, C.byref(cfg), wav.ctypes.data_as(_dp), len(wav),

@@ -1,5 +1,6 @@
-"""Host-side file codecs around the GPU path: WAV (16-bit PCM), PNG containers (8-bit via PIL,
-16-bit via a small zlib writer/reader), float16 metadata bytes, pad bookkeeping.
+"""Host-side file codecs around the GPU path: WAV and FLAC readers in the reference's two flavours (Go: beep /
+mewkiz-flac semantics; Python: soundfile semantics), PNG containers (8-bit via PIL, 16-bit via a small zlib
+writer/reader), float16 metadata bytes, pad bookkeeping.
 
 Only container work and metadata packing happen here; every per-pixel float operation of
 dumpimage / loadpng runs on the GPU through gomel_quantise / gomel_dequantise.
@@ -58,33 +59,95 @@ def unpack_f16(b):
     return float(np.frombuffer(bytes(b), np.float16)[0])
 
 
-# ---------------------------------------------------------------- WAV
+# ---------------------------------------------------------------- WAV / FLAC
+def _wav_pcm(path):
+    """-> (int64 samples (n, channels), sample width in bytes, sample rate, is_float) of a RIFF/WAVE file"""
+    with wave.open(path, "rb") as w:
+        nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        raw = w.readframes(n)
+    if sw == 2:
+        v = np.frombuffer(raw, "<i2").astype(np.int64)
+    elif sw == 1:
+        v = np.frombuffer(raw, np.uint8).astype(np.int64)            # unsigned in the container
+    elif sw == 3:
+        b = np.frombuffer(raw, np.uint8).reshape(-1, 3).astype(np.int64)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        v = np.where(v >= 1 << 23, v - (1 << 24), v)
+    else:
+        v = np.frombuffer(raw, "<i4").astype(np.int64)
+    return v.reshape(-1, nch), sw, sr
+
+
 def load_wav(path):
-    """loadwav (mel/impl.go:234-264): left channel of a PCM WAV as float64 in [-1,1), sample rate"""
+    """Go flavour -- loadwav (mel/impl.go:234-264, phase/impl.go:309-349) over faiface/beep v1.1.0 wav.Decode: LEFT
+    channel only; 8-bit p/255*2-1, 16-bit v/(2^15-1), 24-bit v/(2^23-1); returns (float64 samples, sample rate)"""
     try:
-        with wave.open(path, "rb") as w:
-            nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
-            raw = w.readframes(n)
+        v, sw, sr = _wav_pcm(path)
     except (OSError, wave.Error, EOFError) as e:
         print(e)
         return np.zeros(0), 0.0
+    left = v[:, 0].astype(np.float64)
     if sw == 2:
-        a = np.frombuffer(raw, "<i2").astype(np.float64) / 32767.0   # beep v1.1.0 wav decode scales by 2^15-1
+        a = left / 32767.0
     elif sw == 1:
-        a = (np.frombuffer(raw, np.uint8).astype(np.float64) - 128.0) / 128.0
+        a = left / 255.0 * 2.0 - 1.0
     elif sw == 3:
-        b = np.frombuffer(raw, np.uint8).reshape(-1, 3).astype(np.int32)
-        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
-        a = np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float64) / float(1 << 23)
+        a = left / float((1 << 23) - 1)
     else:
-        a = np.frombuffer(raw, "<i4").astype(np.float64) / float(1 << 31)
-    return np.ascontiguousarray(a.reshape(-1, nch)[:, 0]), float(sr)
+        a = left / float((1 << 31) - 1)            # beyond beep v1.1.0 (8/16/24 only); same rule extended
+    return np.ascontiguousarray(a), float(sr)
+
+
+def load_wav_sf(path):
+    """Python flavour -- load_wav_with_sr (phase.py:551-567) over soundfile.read(dtype='float64'): integer PCM
+    scaled by 1/2^(bits-1) (8-bit: (p-128)/128), channels AVERAGED; returns (float64 samples, int sample rate)"""
+    v, sw, sr = _wav_pcm(path)
+    x = v.astype(np.float64)
+    a = (x - 128.0) / 128.0 if sw == 1 else x / float(1 << (8 * sw - 1))
+    a = a[:, 0] if a.shape[1] == 1 else np.mean(a, axis=1)
+    return np.ascontiguousarray(a), int(sr)
+
+
+def load_flac_go(path, scale):
+    """Go flavour -- loadflac (mel/impl.go:266-296: scale 256*256; phase/impl.go:351-381: scale 256*128) over
+    mewkiz/flac: every frame's subframes are appended one after the other -- block of channel 0, block of channel 1,
+    next frame ... -- NOT interleaved and not mixed down; integer sample / scale.  Returns (samples, sample rate)."""
+    from . import flac
+    try:
+        blocks, sr, _, _ = flac.decode(path)
+    except (OSError, flac.FlacError, EOFError, IndexError) as e:
+        print(e)
+        return np.zeros(0), 0.0
+    if not blocks:
+        return np.zeros(0), float(sr)
+    out = np.concatenate([ch for blk in blocks for ch in blk]).astype(np.float64) / float(scale)
+    return out, float(sr)
+
+
+def load_flac_sf(path):
+    """Python flavour -- load_flac_with_sr (phase.py:570-586) over soundfile: sample / 2^(bits-1), channels averaged"""
+    from . import flac
+    blocks, sr, bps, nch = flac.decode(path)
+    if not blocks:
+        return np.zeros(0), int(sr)
+    x = np.stack([np.concatenate([blk[c] for blk in blocks]) for c in range(nch)], axis=1).astype(np.float64)
+    x /= float(1 << (bps - 1))
+    a = x[:, 0] if nch == 1 else np.mean(x, axis=1)
+    return np.ascontiguousarray(a), int(sr)
 
 
 def save_wav(path, data, sr):
-    """dumpwav (mel/impl.go:195-232): mono 16-bit PCM; beep clamps to [-1,1] and scales by 2^15-1"""
+    """Go flavour -- dumpwav (mel/impl.go:195-232): mono 16-bit PCM; beep clamps to [-1,1], scales by 2^15-1 and
+    TRUNCATES (int16(v * 32767))"""
     x = np.clip(np.asarray(data, np.float64), -1.0, 1.0)
     save_wav_pcm16(path, (x * 32767.0).astype("<i2"), sr)
+
+
+def save_wav_sf(path, data, sr):
+    """Python flavour -- save_wav (phase.py:589-601): clip to [-1,1], soundfile.write(subtype='PCM_16'), i.e.
+    libsndfile's double -> short conversion lrint(x * 0x7FFF): ROUND to nearest even"""
+    x = np.clip(np.asarray(data, np.float64), -1.0, 1.0)
+    save_wav_pcm16(path, np.rint(x * 32767.0).astype("<i2"), sr)
 
 
 def save_wav_pcm16(path, pcm, sr):

@@ -96,6 +96,16 @@ class Mel:
         codec.mel_dump_image(outputFile, ospectrum, self.NumMels, self.YReverse,
                              float(len(buf) * self.NumMels) / float(len(ospectrum)), float(sr), device=self.Device)
 
+    def ToMelFlac(self, inputFile, outputFile):
+        """mel.ToMelFlac (mel/mel.go:176-192): loadflac scales samples by 1/65536 here (mel/impl.go:290) -- half the
+        amplitude of the phase package's loader; kept"""
+        buf, sr = codec.load_flac_go(inputFile, 256 * 256)
+        if len(buf) == 0:
+            raise ErrFileNotLoaded()
+        ospectrum = self.ToMel(buf)
+        codec.mel_dump_image(outputFile, ospectrum, self.NumMels, self.YReverse,
+                             float(len(buf) * self.NumMels) / float(len(ospectrum)), float(sr), device=self.Device)
+
     def ToWavPng(self, inputFile, outputFile):
         buf, samples, samplerate = codec.mel_load_png(inputFile, self.YReverse, device=self.Device)
         if len(buf) == 0:
@@ -112,6 +122,11 @@ class Mel:
 def NewMel():
     """mel.NewMel (mel/mel.go:30-41)"""
     return Mel()
+
+
+def LoadFlac(inputFile):
+    """mel.LoadFlac (mel/mel.go:155-158)"""
+    return codec.load_flac_go(inputFile, 256 * 256)[0]
 
 
 def LoadWav(inputFile):

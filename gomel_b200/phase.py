@@ -98,6 +98,22 @@ class Phase:
         save_image(output_file, spectrogram, self.num_freqs, samples_in_mel, sample_rate, self.y_reverse,
                    self.HDR, self.IHS, device=self.device)
 
+    def _flac_spectrogram(self, input_file):
+        audio, sample_rate = load_flac_with_sr(input_file)
+        audio, sample_rate = self._prepare(audio, sample_rate, update_rate=True)       # phase.py:267-276, :303-312
+        return audio, sample_rate, self.to_phase(audio)
+
+    def to_phase_flac(self, input_file, output_file):
+        """phase.py:255-288: like to_phase_wav, but the embedded sample rate follows the zero-stuffing ratio"""
+        audio, sample_rate, spectrogram = self._flac_spectrogram(input_file)
+        samples_in_mel = float(len(audio) * self.num_freqs) / float(len(spectrogram))
+        save_image(output_file, spectrogram, self.num_freqs, samples_in_mel, sample_rate, self.y_reverse,
+                   self.HDR, self.IHS, device=self.device)
+
+    def to_tensor_flac(self, input_file):
+        """phase.py:291-318: FLAC file -> spectrogram array, nothing written"""
+        return self._flac_spectrogram(input_file)[2]
+
     def to_wav_png(self, input_file, output_file):
         spectrogram, samples, embedded_sample_rate, self.num_freqs = load_image(
             input_file, self.y_reverse, self.HDR, self.IHS, device=self.device)
@@ -124,6 +140,30 @@ class Phase:
         """phase.ToPhase (phase/phase.go:41-70)"""
         return self.to_phase(buf)
 
+    def _go_to_png(self, buf, sr, output_file):
+        """body shared by phase.ToPhaseFlac / ToPhaseWav (phase/phase.go:195-244): the Go package keeps the length
+        BEFORE zero stuffing for the metadata, pads / shifts by the Go table (phase/impl.go:476-507)"""
+        if len(buf) == 0:
+            raise ErrFileNotLoaded()
+        original = len(buf)
+        zp, zs = GO_PAD_SHIFT.get(int(sr), (0, 0))            # padShift: unknown rates -> no stuffing, no error
+        if zp > 0:
+            buf = zero_stuff_upsample(buf, zp, zs)
+        spec = self.to_phase(buf)
+        codec.phase_dump_image_go(output_file, spec, self.num_freqs, self.y_reverse,
+                                  float(original * self.num_freqs) / float(len(spec)), float(sr), self.ihsPasses(),
+                                  self.HDR, device=self.device)
+
+    def ToPhaseFlac(self, inputFile, outputFile):
+        """phase.ToPhaseFlac (phase/phase.go:195-219): loadflac scales by 1/32768 (phase/impl.go:375)"""
+        buf, sr = codec.load_flac_go(inputFile, 256 * 128)
+        self._go_to_png(buf, sr, outputFile)
+
+    def ToPhaseWav(self, inputFile, outputFile):
+        """phase.ToPhaseWav (phase/phase.go:221-244)"""
+        buf, sr = codec.load_wav(inputFile)
+        self._go_to_png(buf, sr, outputFile)
+
     def FromPhase(self, ospectrum):
         """phase.FromPhase (phase/phase.go:136-153): boost applied iff != 0 (phase/phase.go:146)"""
         return _lib.default_context(self.device).from_phase(self._cfg(self.volume_boost), ospectrum)
@@ -135,6 +175,11 @@ class Phase:
     def ihsPasses(self):
         """phase/phase.go:31-36"""
         return 2 if (self.IHS and not self.HDR) else 0
+
+
+# padShift (phase/impl.go:476-507)
+GO_PAD_SHIFT = {48000: (0, 0), 32000: (2, 1), 24000: (1, 1), 16000: (1, 2), 8000: (1, 5),
+                44100: (0, 0), 22050: (1, 1), 11025: (1, 3)}
 
 
 def NewPhase():
@@ -173,18 +218,34 @@ def zero_stuff_upsample(audio, zero_pad, zero_shift):
     return output
 
 
+class ErrFileNotLoaded(Exception):
+    """phase.ErrFileNotLoaded (phase/phase.go:38)"""
+
+    def __init__(self):
+        super().__init__("wavNotLoaded")
+
+
 def load_wav_with_sr(file_path):
-    a, sr = codec.load_wav(file_path)
-    return a, int(sr)
+    """phase.py:551-567 (soundfile semantics: /2^(bits-1), channels averaged)"""
+    return codec.load_wav_sf(file_path)
+
+
+def load_flac_with_sr(file_path):
+    """phase.py:570-586 (soundfile semantics; the FLAC container is decoded by gomel_b200/flac.py)"""
+    return codec.load_flac_sf(file_path)
 
 
 def load_wav(file_path):
-    return codec.load_wav(file_path)[0]
+    return codec.load_wav_sf(file_path)[0]
+
+
+def load_flac(file_path):
+    return codec.load_flac_sf(file_path)[0]
 
 
 def save_wav(file_path, audio_buffer, sample_rate):
-    """phase.py:589-601: clip to [-1,1], 16-bit PCM mono"""
-    codec.save_wav(file_path, audio_buffer, sample_rate)
+    """phase.py:589-601: clip to [-1,1], 16-bit PCM mono through libsndfile's rounding conversion"""
+    codec.save_wav_sf(file_path, audio_buffer, sample_rate)
 
 
 pack_float16_to_bytes = codec.pack_f16_py

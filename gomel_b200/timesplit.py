@@ -65,10 +65,18 @@ class Session:
             assert len(init_local) == self.n_samples
             d_init = ctx.dev_malloc(init_local.nbytes)
             ctx.h2d(d_init, init_local)
-        ctx.check(ctx.lib.gomel_ts_load(self.h, d_mel, d_init, seed))
+        self.load_dev(d_mel, d_init, seed)
         ctx.dev_free(d_mel)
         if d_init is not None:
             ctx.dev_free(d_init)
+
+    def load_dev(self, d_mel_local, d_init_local=None, seed=0):
+        """as load(), from device-resident float32 buffers: computes this rank's target magnitudes (both precisions
+        the policy needs) and the start signal -- the once-per-FromMel part of the work"""
+        self.ctx.check(self.ctx.lib.gomel_ts_load(self.h, d_mel_local, d_init_local, seed))
+
+    def lead_iters(self):
+        return int(self.ctx.lib.gomel_ts_lead_iters(self.h))
 
     def iterate(self, it, part=0):
         self.ctx.check(self.ctx.lib.gomel_ts_iterate(self.h, it, part))
