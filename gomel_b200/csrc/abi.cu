@@ -92,6 +92,7 @@ struct gomel_ctx {
     unsigned long long launches = 0;
     int tile_override = 0;
     int gl_tile_waves = 4;            // Griffin-Lim: CTA waves per iteration the automatic tiling aims at
+    int gl_stateless = 0;             // GOMEL_GL_STATELESS: float32 iterations on k_gl_iter_s (3 CTAs / SM) -- A/B knob
     std::string err;
     std::mutex mu;
 };
@@ -169,14 +170,15 @@ long pad_len(long n, int filter)            // mel/impl.go:429-455
 // waves: CTA waves per launch the automatic tiling aims at.  Single launches (forward / phase kernels) want
 // many short waves (small tail); Griffin-Lim iterations run as two interleaved groups that cover each other's
 // tails, so they take longer tiles (less per-tile prologue)
-Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len, int t_floor = 4, int waves = 8)
+Tiling make_tiling(gomel_ctx* ctx, int n_clips, long n_frames, long sig_stride, long sig_len, int t_floor = 4, int waves = 8,
+                   int ctas_per_sm = 2)
 {
     Tiling tl;
     tl.n_frames = (int)n_frames;
     int T;
     if (ctx->tile_override > 0) T = ctx->tile_override;
     else {
-        const long slots = 2L * ctx->sm_count;
+        const long slots = (long)ctas_per_sm * ctx->sm_count;
         long tiles_wanted = (waves * slots + n_clips - 1) / n_clips;
         if (tiles_wanted < 1) tiles_wanted = 1;
         T = (int)((n_frames + tiles_wanted - 1) / tiles_wanted);
@@ -336,11 +338,12 @@ int ensure_tables_d64(gomel_ctx* ctx)
             const double a = two_pi * (double)((t * pw[i]) % 4096) / 4096.0;
             T1[(i * 256 + t) * 2] = std::cos(a); T1[(i * 256 + t) * 2 + 1] = -std::sin(a);
         }
-        for (int n0 = 0; n0 < 16; n0++) {
-            const double a = two_pi * (double)((n0 * pw[i]) % 256) / 256.0;
-            T2[(i * 16 + n0) * 2] = std::cos(a); T2[(i * 16 + n0) * 2 + 1] = -std::sin(a);
-        }
     }
+    for (int k = 0; k < 16; k++)                     // stage 2: full table W256^(n0*k)
+        for (int n0 = 0; n0 < 16; n0++) {
+            const double a = two_pi * (double)((n0 * k) % 256) / 256.0;
+            T2[(k * 16 + n0) * 2] = std::cos(a); T2[(k * 16 + n0) * 2 + 1] = -std::sin(a);
+        }
     for (int n = 0; n < kN / 2; n++) win[n] = 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1)));
     CU(cudaMalloc(&ctx->d_tables_d64, D::kTableBytes));
     CU(cudaMemcpy(ctx->d_tables_d64, blob.data(), D::kTableBytes, cudaMemcpyHostToDevice));
@@ -379,7 +382,8 @@ int gl_reserve(gomel_ctx* ctx, const gomel_config* cfg, int n_clips, long n_fram
     void* b;
     const size_t sig_bytes = (size_t)n_clips * sig_stride * 4;
     const Tiling tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves);
-    const size_t hb_elems = (size_t)n_clips * (tl.n_tiles + 1) * geo.halo + 4;
+    const Tiling tl3 = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves, 3);
+    const size_t hb_elems = (size_t)n_clips * ((tl.n_tiles > tl3.n_tiles ? tl.n_tiles : tl3.n_tiles) + 1) * geo.halo + 4;
     if (need_init) { if (int rc = ensure(ctx, S_INIT, sig_bytes, &b)) return rc; }
     if (iters - lead > 0) {
         if (iters - lead > 1 || lead > 0) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &b)) return rc; }
@@ -395,6 +399,9 @@ int gl_reserve(gomel_ctx* ctx, const gomel_config* cfg, int n_clips, long n_fram
     }
     return 0;
 }
+
+int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl, bool stateless,
+               const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs);
 
 int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips, long n_frames,
            unsigned long long seed, long sig_stride)
@@ -509,7 +516,33 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
         cur32 = conv;
         if (iters == lead) { CU(cudaGetLastError()); return 0; }
     }
-    // ---------------- float32 iterations
+    // ---------------- float32 iterations (a tiling of their own: the hand-over above folded every partial in)
+    const bool stateless = ctx->gl_stateless && !geo.alt;
+    const Tiling tl32 = stateless ? make_tiling(ctx, n_clips, n_frames, sig_stride, ola, 4, ctx->gl_tile_waves, 3) : tl;
+    return gl_dev_f32(ctx, cfg, geo, io, tl32, stateless, cur32, tmp, n_clips, iters, lead, ns, gs);
+}
+
+int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl, bool stateless,
+               const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs)
+{
+    (void)cfg;
+    const int hb_tiles = tl.n_tiles + 1;
+    const long grid = (long)n_clips * tl.n_tiles;
+    auto c_lo = [&](int g) { return (int)((long)n_clips * g / ns); };
+    auto fork = [&]() -> int {
+        if (ns > 1) {
+            CU(cudaEventRecord(ctx->ev_fork, ctx->st));
+            for (int g = 1; g < ns; g++) CU(cudaStreamWaitEvent(gs[g], ctx->ev_fork, 0));
+        }
+        return 0;
+    };
+    auto join = [&]() -> int {
+        for (int g = 1; g < ns; g++) {
+            CU(cudaEventRecord(ctx->ev_join[g - 1], gs[g]));
+            CU(cudaStreamWaitEvent(ctx->st, ctx->ev_join[g - 1], 0));
+        }
+        return 0;
+    };
     SynParams p = {};
     p.tables = geo.alt ? ctx->d_tables_alt : ctx->d_tables;
     p.tl = tl;
@@ -527,6 +560,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
             p.clip0 = c_lo(g);
             const unsigned gg = (unsigned)((long)(c_lo(g + 1) - c_lo(g)) * tl.n_tiles);
             if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+            else if (stateless) k_gl_iter_s<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
             else k_gl_iter<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
             ctx->launches++;
         }
@@ -764,6 +798,8 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_PHASE>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_SPEC>)) return rc;
         CU(cudaFuncSetAttribute(k_gl_iter<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
+        CU(cudaFuncSetAttribute(k_gl_iter_s<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
+        if (const char* e = getenv("GOMEL_GL_STATELESS")) ctx->gl_stateless = atoi(e) != 0;
         if (int rc = set_smem_attr(ctx, k_istft_phase<kHS>)) return rc;
         return 0;
     };

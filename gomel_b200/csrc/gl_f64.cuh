@@ -29,7 +29,8 @@ constexpr int kRow = 17;                                   // double2 cells per 
 constexpr int kPlane = 16 * kRow;                          // 272
 constexpr int kXchgCells = 16 * kPlane;                    // 4352
 constexpr int kXchgBytes = kXchgCells * 16;                // 69,632 B
-constexpr int kT1Cells = 4 * 256, kT2Cells = 4 * 16;       // powers 1,2,4,8 of each lane's root
+constexpr int kT1Cells = 4 * 256;                          // stage 1: powers 1,2,4,8 of each lane's root W4096^t
+constexpr int kT2Cells = 16 * 16;                          // stage 2: all powers of W256^n0 (4 KB: cheaper than 11 products)
 constexpr int kWinCells = 2048;                            // first half of the symmetric Hann window, [m][t]
 constexpr int kTableBytes = (kT1Cells + kT2Cells) * 16 + kWinCells * 8;      // 33,792 B
 constexpr int kScratchBytes = 32 * 16;                     // the special coset's hand-over (warp 0)
@@ -159,6 +160,14 @@ __device__ __forceinline__ void radix16(c64 (&v)[16])
     for (int i = 0; i < 16; i++) v[i] = o[i];
 }
 
+// external twiddles from a full table T[k][lane] = w^k
+template <bool INV>
+__device__ __forceinline__ void apply_twiddles_full(c64 (&v)[16], const c64* T, int rowlen, int lane)
+{
+#pragma unroll
+    for (int k = 1; k < 16; k++) v[k] = cmul_tw<INV>(v[k], T[k * rowlen + lane]);
+}
+
 // external twiddles v[k] *= w^k (forward) or conj(w)^k (inverse); the table holds w^1, w^2, w^4, w^8
 template <bool INV>
 __device__ __forceinline__ void apply_twiddles(c64 (&v)[16], const c64* T, int rowlen, int lane)
@@ -188,7 +197,7 @@ __device__ __forceinline__ void fft_fwd(c64 (&v)[16], const Smem& s, const Lanes
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];
     radix16<false>(v);
-    apply_twiddles<false>(v, s.T2, 16, L.n0b);
+    apply_twiddles_full<false>(v, s.T2, 16, L.n0b);
 #pragma unroll
     for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];
     __syncwarp();                                   // plane k0 is private to this half-warp
@@ -201,7 +210,7 @@ __device__ __forceinline__ void fft_fwd(c64 (&v)[16], const Smem& s, const Lanes
 __device__ __forceinline__ void fft_inv(c64 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<true>(v);
-    apply_twiddles<true>(v, s.T2, 16, L.k1c);
+    apply_twiddles_full<true>(v, s.T2, 16, L.k1c);
 #pragma unroll
     for (int c = 0; c < 16; c++) s.xb[L.base_c + c] = v[c];
     __syncwarp();
@@ -221,11 +230,22 @@ __device__ __forceinline__ c64 shfl2(c64 a, int src)
 {
     return mk(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
+// 1/sqrt(n) to float64 rounding, branch free: float32 MUFU seed (relative error < 2^-22), two Newton steps
+// (error 1.5 e^2 each -> 1e-27 before rounding).  n = |X|^2 of a spectrum of O(1) signals: far inside the float32
+// range; n = 0 gives inf * 0 = NaN, which the caller's n > 0 select discards.
+__device__ __forceinline__ double rsqrt_nr(double n)
+{
+    double y = (double)rsqrtf((float)n);
+    const double h = 0.5 * n;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+}
 // cmplx.Rect(M, cmplx.Phase(X)) (mel/mel.go:98-102): M * X/|X|, Phase(0) = 0 -> (M, 0)
 __device__ __forceinline__ c64 subst(c64 X, double M)
 {
     const double n = fma(X.x, X.x, X.y * X.y);
-    const double r = M * rsqrt(n);
+    const double r = M * rsqrt_nr(n);
     return (n > 0.0) ? mk(X.x * r, X.y * r) : mk(M, 0.0);
 }
 // the two real spectra riding one complex transform, up to a common factor 2 (P = Z[N-k])
@@ -234,7 +254,7 @@ __device__ __forceinline__ c64 split_b(c64 z, c64 P) { return mk(z.y + P.y, P.x 
 __device__ __forceinline__ c64 join_lo(c64 ya, c64 yb) { return mk(ya.x - yb.y, ya.y + yb.x); }
 __device__ __forceinline__ c64 join_hi(c64 ya, c64 yb) { return mk(ya.x + yb.y, yb.x - ya.y); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+using gomel::prefetch_l2;
 
 struct GLParams {
     const double* tables;    // T1 | T2 | win  (kTableBytes)
@@ -341,11 +361,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
                 }
                 __syncwarp();
             }
+            // all sixteen target magnitudes are requested before the first one is used: one L2 round trip per pair
+            // instead of eight
+            double mav[8], mbv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { mav[j] = __ldg(mA + j * 256); mbv[j] = validB ? __ldg(mB + j * 256) : 0.0; }
             c64 nlo[8], nhi[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const double ma = __ldg(mA + j * 256);
-                const double mb = validB ? __ldg(mB + j * 256) : 0.0;
+                const double ma = mav[j];
+                const double mb = mbv[j];
                 const c64 P = shfl2(v[15 - j], L.src);
                 const c64 z = v[j];
                 const c64 ya = subst(split_a(z, P), ma);

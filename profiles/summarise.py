@@ -17,7 +17,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__warps_eligible.avg.per_cycle_active", "sm__cycles_elapsed.avg", "lts__t_bytes.sum"]
+        "smsp__warps_eligible.avg.per_cycle_active", "sm__cycles_elapsed.avg", "lts__t_bytes.sum",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_red.sum",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_warps", "sm__maximum_warps_per_active_cycle_pct"]
 
 
 def ncu(args):
@@ -26,10 +30,15 @@ def ncu(args):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    ksel, alg_bytes = [], 18436
+    if "--kernel" in sys.argv:          # regex on the kernel name when a report holds several kernels
+        ksel = ["-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1]]
+    if "--alg-bytes" in sys.argv:
+        alg_bytes = int(sys.argv[sys.argv.index("--alg-bytes") + 1])
     frame_iters = None
     if "--frame-iters" in sys.argv:
         frame_iters = int(sys.argv[sys.argv.index("--frame-iters") + 1])
-    rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
+    rows = list(csv.reader(io.StringIO(ncu(["-i", rep] + ksel + ["--page", "raw", "--csv"]))))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     res = {"report": rep, "kernel": data[0][col["Kernel Name"]], "launches_captured": len(data), "metrics": {}}
@@ -43,9 +52,9 @@ def main():
     if frame_iters:
         res["frame_iters_per_launch"] = frame_iters
         res["dram_bytes_per_frame_iter"] = (rd + wr) / frame_iters
-        res["algorithmic_bytes_per_frame_iter"] = 18436
+        res["algorithmic_bytes_per_frame_iter"] = alg_bytes
     # stall reasons + opcode mix from the source page
-    src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
+    src = list(csv.reader(io.StringIO(ncu(["-i", rep] + ksel + ["--page", "source", "--csv", "--print-source", "sass"]))))
     hidx = [i for i, r in enumerate(src) if r and r[0] == "Address"]
     h = src[hidx[0]]
     end = hidx[1] - 1 if len(hidx) > 1 else len(src)
@@ -81,7 +90,7 @@ def main():
             f.write(f"| {k} | {v['unit']} | {', '.join(v['values'])} |\n")
         f.write(f"\nDRAM bytes per launch: {res['dram_bytes_per_launch']:.4g}")
         if frame_iters:
-            f.write(f" = {res['dram_bytes_per_frame_iter']:.0f} B per frame-iteration (algorithmic 18,436)")
+            f.write(f" = {res['dram_bytes_per_frame_iter']:.0f} B per frame-iteration (algorithmic {alg_bytes:,})")
         f.write(f"\n\nSASS lines: {res['sass_lines']}, warp instructions executed: {ti}\n\n## stall samples (%)\n\n")
         for k, v in res["stall_samples_pct"].items():
             f.write(f"* {k}: {v}\n")
