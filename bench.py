@@ -338,6 +338,54 @@ def timesplit_measure(ctx, cfg, rank, local_rank, world, use_dist, seconds, step
         "gpu_launches": int(launches)}
 
 
+def timesplit_phase_measure(ctx, rank, world, use_dist, seconds, steps, tile=64):
+    """SURVEY 8(e) third case: phase.ISTFT of ONE long clip (NumFreqs 768), frames split by time over the ranks, one
+    NCCL transfer of 2816 floats per rank boundary (gomel_ts_phase_run_nccl).  Device-resident spectrogram slices."""
+    from gomel_b200 import _lib, timesplit
+    if use_dist:
+        import torch
+        import torch.distributed as dist
+    nfq = 768
+    pcfg = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=0, n_freqs=nfq, gl_iters=0)
+    n_total = int(round(seconds * SR))
+    _, frames_total, ola = _lib.frames(pcfg, n_total)
+    s = timesplit.Session(ctx, pcfg, frames_total, rank, world, tile, 0)
+    rng = np.random.default_rng(77 + rank)
+    base = rng.standard_normal((2048, nfq * 2)).astype(np.float32)
+    spec = np.ascontiguousarray(base[np.arange(s.n_frames) % 2048])
+    d_spec, d_out = ctx.dev_malloc(spec.nbytes), ctx.dev_malloc(s.n_samples * 4)
+    ctx.h2d(d_spec, spec)
+    timesplit.NativeNccl(s)
+
+    def barrier():
+        s.sync()
+        if use_dist:
+            torch.cuda.synchronize()
+            dist.barrier()
+    for _ in range(2):
+        ctx.check(ctx.lib.gomel_ts_phase_run_nccl(s.h, d_spec, d_out))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.check(ctx.lib.gomel_ts_phase_run_nccl(s.h, d_spec, d_out))
+    s.sync()
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    if use_dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    s.close()
+    ctx.dev_free(d_spec)
+    ctx.dev_free(d_out)
+    peak, _ = peaks()
+    fps = frames_total * steps / (ms / 1e3)
+    return {"workload": f"phase.ISTFT of one {seconds:.0f} s clip ({frames_total} frames, NumFreqs {nfq}) split by time over {world} GPU(s), "
+                        f"one NCCL transfer of 2816 floats per boundary, tile {tile} frames; host clock, max over ranks",
+            "ms_per_step": ms / steps, "frames_per_s": fps, "audio_s_per_s": frames_total * HOP / SR * steps / (ms / 1e3),
+            "hbm_frac_whole_job": fps * 11264 / 1e9 / (peak * world), "scaling": "strong"}
+
+
 def parity_record(ctx, cfg, _lib, base_mel, frames, ola, n=4):
     """rel-L2 of n bench clips through the benchmarked call (gomel_from_mel_batch_host, default precision policy,
     injected start signals) against the all-float64 fused kernel on the same inputs -- the number the north-star
@@ -543,6 +591,10 @@ def run_product(args):
         ts = timesplit_measure(ctx, cfg, rank, local_rank, world, use_dist, args.timesplit_seconds, max(1, min(args.steps, 3)), 1,
                                args.ts_tile, args.ts_edge, args.ts_overlap, args.ts_exchange)
 
+        ts_phase = timesplit_phase_measure(ctx, rank, world, use_dist, args.timesplit_seconds, max(1, min(args.steps, 3)))
+    else:
+        ts_phase = None
+
     audio_s_per_step = world * clips * frames * HOP / SR          # seconds of audio covered by the frames
     value = audio_s_per_step * args.steps / (dev_ms / 1e3)
     e2e_value = audio_s_per_step * args.steps / (e2e_ms / 1e3)
@@ -613,7 +665,7 @@ def run_product(args):
                           "other_modes_device_resident": modes},
             "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "host_link": link, "strong_1024": strong, "timesplit": ts,
+            "host_link": link, "strong_1024": strong, "timesplit": ts, "timesplit_phase_istft": ts_phase,
             "stft_frames_per_s": frame_iters * world * args.steps / (dev_ms / 1e3),
             "stft_frames_per_s_note": "Griffin-Lim frame-iterations (one analysis STFT + one synthesis ISTFT each) per second, whole job",
         }

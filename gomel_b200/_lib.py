@@ -88,6 +88,10 @@ SIGNATURES = {
     "gomel_nccl_unique_id": (C.c_int, [_vp, C.c_char_p]),
     "gomel_ts_nccl_init": (C.c_int, [_vp, C.c_char_p]),
     "gomel_ts_run_nccl": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "gomel_ts_phase_istft": (C.c_int, [_vp, _vp]),
+    "gomel_ts_phase_halo_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "gomel_ts_phase_finish": (C.c_int, [_vp, _vp]),
+    "gomel_ts_phase_run_nccl": (C.c_int, [_vp, _vp, _vp]),
     "gomel_copy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "gomel_from_mel_batch_host": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, _vp, C.c_int]),
     "gomel_from_mel_batch_host_pcm16": (C.c_int, [_vp, _cp, _vp, C.c_int, C.c_long, _vp, C.c_ulonglong, _vp, C.c_int]),

@@ -649,6 +649,7 @@ int from_phase_dev_impl(gomel_ctx* ctx, const gomel_config* cfg, const float* d_
     p.spec = reinterpret_cast<const float2*>(d_spec); p.n_freqs = cfg->n_freqs;
     p.gain_head = ctx->d_gain_head; p.gain_mid = ctx->d_gain_mid; p.gain_tail = ctx->d_gain_tail;
     p.head_len = ctx->gain_head_len; p.tail_len = ctx->gain_tail_len;
+    p.gain_off = 0; p.total_len = ola;
     void* hb;
     p.hb_tiles = p.tl.n_tiles + 1; p.tile_lo = 0; p.tiles_in_launch = p.tl.n_tiles;
     if (int rc = ensure(ctx, S_HB0, (size_t)n_clips * p.hb_tiles * kHalo * 4 + 16, &hb)) return rc;
@@ -1463,7 +1464,7 @@ struct gomel_ts {
     gomel_ctx* ctx = nullptr;
     gomel_config cfg;
     int rank = 0, world = 1;
-    long f_begin = 0, n_local = 0, sample_begin = 0, n_samples = 0;
+    long f_begin = 0, n_local = 0, sample_begin = 0, n_samples = 0, n_frames_total = 0;
     Tiling tl;
     int ext_prev = 0, ext_next = 0;
     float *sig[2] = { nullptr, nullptr }, *hb[2] = { nullptr, nullptr }, *mags = nullptr;
@@ -1494,7 +1495,7 @@ int gomel_ts_create2(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_tota
     if (tiles_total < world) return fail(ctx, GOMEL_E_ARG, "fewer tiles than ranks: lower tile_frames");
     const long a = rank * tiles_total / world, b = (rank + 1) * tiles_total / world;
     gomel_ts* ts = new gomel_ts();
-    ts->ctx = ctx; ts->cfg = *cfg; ts->rank = rank; ts->world = world;
+    ts->ctx = ctx; ts->cfg = *cfg; ts->rank = rank; ts->world = world; ts->n_frames_total = n_frames_total;
     ts->f_begin = a * T;
     const long f_end = (b * T < n_frames_total) ? b * T : n_frames_total;
     ts->n_local = f_end - ts->f_begin;
@@ -1759,6 +1760,71 @@ int gomel_ts_finish(gomel_ts* ts, int iters, float* d_out_local)
     return 0;
 }
 
+// ---- phase.ISTFT of one long clip split by time (SURVEY 8(e) third case; phase/phase.go:93-133) -------------
+// Each rank inverts its own frames; a sample next to a rank boundary is the sum of the earlier rank's tail partial
+// and the later rank's head partial, and it belongs to the later rank: ONE transfer of 2816 floats per boundary
+// (tail -> next rank), then the window-sum gain -- a function of the global sample index, max(sum w^2) in closed
+// form from the host tables of prepare_gain -- is applied by the owner.
+static SynParams ts_phase_params(gomel_ts* ts)
+{
+    gomel_ctx* ctx = ts->ctx;
+    SynParams p = {};
+    p.tables = ctx->d_tables; p.tl = ts->tl;
+    p.sig_out = ts->sig[0]; p.hb_out = ts->hb[0];
+    p.n_freqs = ts->cfg.n_freqs;
+    p.gain_head = ctx->d_gain_head; p.gain_mid = ctx->d_gain_mid; p.gain_tail = ctx->d_gain_tail;
+    p.head_len = ctx->gain_head_len; p.tail_len = ctx->gain_tail_len;
+    p.hb_tiles = ts->tl.n_tiles + 1; p.tile_lo = 0; p.tiles_in_launch = ts->tl.n_tiles;
+    p.ext_prev = ts->ext_prev; p.ext_next = ts->ext_next;
+    p.gain_off = ts->sample_begin; p.total_len = kN + (ts->n_frames_total - 1) * (long)kHop;
+    return p;
+}
+
+int gomel_ts_phase_istft(gomel_ts* ts, const float* d_spec_local)
+{
+    if (!ts || !d_spec_local) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    if (ts->cfg.n_freqs <= 0 || ts->cfg.n_freqs > kN / 2) return fail(ctx, GOMEL_E_ARG, "NumFreqs out of range");
+    if (ts->tl.edge_first || ts->tl.edge_last) return fail(ctx, GOMEL_E_ARG, "phase ISTFT sessions use uniform tiles (edge_frames = 0)");
+    if (int rc = prepare_gain(ctx, ts->n_frames_total, ts->cfg.volume_boost)) return rc;
+    SynParams p = ts_phase_params(ts);
+    p.spec = reinterpret_cast<const float2*>(d_spec_local);
+    k_istft_phase<kHS><<<(unsigned)ts->tl.n_tiles, kThreads, kFwdSmemBytes, ctx->st>>>(p);
+    ctx->launches++;
+    CU(cudaEventRecord(ts->ev_edge, ctx->st)); ts->have_edge = true;      // the exchange waits for this (gomel_ts_comm_begin)
+    ts->have_comm = false;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int gomel_ts_phase_halo_ptrs(gomel_ts* ts, float** send_tail, float** recv_tail)
+{
+    if (!ts) return GOMEL_E_ARG;
+    if (send_tail) *send_tail = ts->ext_next ? ts->sig[0] + ts->n_local * kHop : nullptr;
+    if (recv_tail) *recv_tail = ts->ext_prev ? ts->sig[0] : nullptr;
+    return 0;
+}
+
+int gomel_ts_phase_finish(gomel_ts* ts, float* d_out_local)
+{
+    if (!ts || !d_out_local) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    Guard g(ctx);
+    if (ts->have_comm) CU(cudaStreamWaitEvent(ctx->st, ts->ev_comm, 0));
+    const int t_first = ts->ext_prev ? 0 : 1;
+    if (ts->tl.n_tiles - t_first > 0) {
+        SynParams p = ts_phase_params(ts);
+        k_halo_fix<<<(unsigned)(ts->tl.n_tiles - t_first), 256, 0, ctx->st>>>(ts->sig[0], ts->hb[0], ts->tl, kHop, kHalo, 1, t_first,
+                                                                            ts->tl.n_tiles + 1, p);
+        ctx->launches++;
+    }
+    CU(cudaMemcpyAsync(d_out_local, ts->sig[0], (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int gomel_ts_create(gomel_ctx* ctx, const gomel_config* cfg, long n_frames_total, int rank, int world,
                     int tile_frames, gomel_ts** out)
 {
@@ -1895,6 +1961,29 @@ int gomel_ts_run_nccl(gomel_ts* ts, int first_iter, int n_iters, int overlap)
         if (overlap) { if (int rc = gomel_ts_iterate(ts, it, 2)) return rc; }
     }
     return 0;
+}
+
+int gomel_ts_phase_run_nccl(gomel_ts* ts, const float* d_spec_local, float* d_out_local)
+{
+    if (!ts) return GOMEL_E_ARG;
+    gomel_ctx* ctx = ts->ctx;
+    if (ts->world > 1 && !ts->nccl_comm) { Guard g(ctx); return fail(ctx, GOMEL_E_STATE, "gomel_ts_nccl_init has not been called"); }
+    if (int rc = gomel_ts_phase_istft(ts, d_spec_local)) return rc;
+    {
+        Guard g(ctx);
+        CU(cudaStreamWaitEvent(ts->st_comm, ts->ev_edge, 0));
+        float *send_tail, *recv_tail;
+        gomel_ts_phase_halo_ptrs(ts, &send_tail, &recv_tail);
+        if (ts->world > 1) {
+            int rc = g_nccl.GroupStart();
+            if (!rc && recv_tail) rc = g_nccl.Recv(recv_tail, kHalo, 7 /* ncclFloat */, ts->rank - 1, ts->nccl_comm, ts->st_comm);
+            if (!rc && send_tail) rc = g_nccl.Send(send_tail, kHalo, 7, ts->rank + 1, ts->nccl_comm, ts->st_comm);
+            const int rc2 = g_nccl.GroupEnd();
+            if (rc || rc2) return fail(ctx, GOMEL_E_CUDA, std::string("NCCL halo exchange: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc ? rc : rc2) : "error"));
+        }
+        CU(cudaEventRecord(ts->ev_comm, ts->st_comm)); ts->have_comm = true;
+    }
+    return gomel_ts_phase_finish(ts, d_out_local);
 }
 
 }  // extern "C"

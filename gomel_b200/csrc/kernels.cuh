@@ -448,6 +448,9 @@ struct SynParams {
     int edge_mode, edge_tile0, edge_tile1;   // edge_mode: grid = 1 or 2 CTAs mapped to these tiles
     int ext_prev, ext_next;  // a previous / next rank continues the clip beyond this buffer
     int clip0;               // first clip of this launch (a batch is split over concurrent streams by clip)
+    // phase ISTFT of one rank's slice of a long clip: the window-sum gain is a function of the GLOBAL sample index
+    long gain_off;           // global index of local sample 0 (a multiple of the hop); 0 = whole clip here
+    long total_len;          // length of the whole clip's signal
 };
 
 __device__ __forceinline__ float rsqrt_fast(float x)       // one MUFU.RSQ; callers guarantee x >= 1e-36 (no denormal path)
@@ -830,8 +833,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_gl_iter_s(const SynParams p)
 // mid_idx = s_abs mod hop, supplied by the caller (cheap where hop is a compile-time constant)
 __device__ __forceinline__ float gain_at(const SynParams& p, long s_abs, int mid_idx)
 {
+    s_abs += p.gain_off;
     if (s_abs < p.head_len) return __ldg(p.gain_head + s_abs);
-    const long tail0 = p.tl.sig_len - p.tail_len;
+    const long tail0 = p.total_len - p.tail_len;
     if (s_abs >= tail0) return __ldg(p.gain_tail + (s_abs - tail0));
     return __ldg(p.gain_mid + mid_idx);
 }
@@ -852,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     const long sbase = (long)f0 * H;
     float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
     const long lim = p.tl.sig_len - sbase;
-    const bool has_prev = tile > 0, has_next = (tile + 1) < p.tl.n_tiles;
+    const bool has_prev = tile > 0 || p.ext_prev, has_next = (tile + 1) < p.tl.n_tiles || p.ext_next;
     float* __restrict__ hout = p.hb_out + ((long)clip * p.hb_tiles + tile) * HALO;
     const int t = L.t, nfq = p.n_freqs;
 
@@ -872,7 +876,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
     float gm[SH];
 #pragma unroll
     for (int j = 0; j < SH; j++) gm[j] = __ldg(p.gain_mid + (j * 256 + t) % H);
-    const long mid_lo = p.head_len, mid_hi = p.tl.sig_len - p.tail_len;
+    const long mid_lo = p.head_len - p.gain_off, mid_hi = p.total_len - p.tail_len - p.gain_off;     // local coordinates
     // the first kPre*256 entries of a pair's two spectrogram rows are prefetched into registers one pair ahead
     constexpr int kPre = 6;                                   // covers NumFreqs <= 768
     float2 pre[kPre];

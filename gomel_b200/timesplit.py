@@ -188,6 +188,66 @@ class NativeNccl:
         self.s.ctx.check(self.s.ctx.lib.gomel_ts_run_nccl(self.s.h, first_iter, n_iters, int(overlap)))
 
 
+# ---------------------------------------------------------------- phase.ISTFT of a long clip (third case)
+def phase_istft_local(ctx, cfg, spec, world, tile_frames=16):
+    """FromPhase of ONE clip with the frames split over `world` emulated ranks (sessions of one process, one GPU):
+    every rank inverts its frames, the tail partial of rank r is copied into the head region of rank r+1 (what
+    NCCL does between GPUs), the owner adds it and applies the window-sum gain.  Returns the stitched float32 signal."""
+    spec = np.ascontiguousarray(spec, np.float32).reshape(-1, 2)
+    n_frames = len(spec) // cfg.n_freqs
+    sessions = [Session(ctx, cfg, n_frames, r, world, tile_frames, 0) for r in range(world)]
+    bufs = []
+    try:
+        for s in sessions:
+            part = np.ascontiguousarray(spec[s.frame_begin * cfg.n_freqs:(s.frame_begin + s.n_frames) * cfg.n_freqs])
+            d = ctx.dev_malloc(part.nbytes)
+            ctx.h2d(d, part)
+            bufs.append(d)
+            ctx.check(ctx.lib.gomel_ts_phase_istft(s.h, d))
+        for s in sessions:
+            s.sync()
+        ptrs = []
+        for s in sessions:
+            a, b = C.c_void_p(), C.c_void_p()
+            ctx.check(ctx.lib.gomel_ts_phase_halo_ptrs(s.h, C.byref(a), C.byref(b)))
+            ptrs.append((a.value, b.value))
+        for s in sessions:
+            s.comm_begin(0)
+        for r in range(world - 1):
+            ctx.check(ctx.lib.gomel_copy_d2d(ctx.h, ptrs[r + 1][1], ptrs[r][0], HALO * 4, sessions[r + 1].comm_stream))
+        for s in sessions:
+            s.comm_end(0)
+        outs = []
+        for s in sessions:
+            d_out = ctx.dev_malloc(s.n_samples * 4)
+            ctx.check(ctx.lib.gomel_ts_phase_finish(s.h, d_out))
+            o = np.empty(s.n_samples, np.float32)
+            ctx.d2h(o, d_out)
+            ctx.dev_free(d_out)
+            outs.append(s.owned(o))
+        return np.concatenate(outs)
+    finally:
+        for d in bufs:
+            ctx.dev_free(d)
+        for s in sessions:
+            s.close()
+
+
+def phase_istft_nccl(session, spec_local):
+    """one rank of the real multi-GPU form: library-owned NCCL (NativeNccl(session) must have been built).
+    spec_local: this rank's (n_frames*n_freqs, 2) float32 rows; returns this rank's local signal (see Session.owned)."""
+    ctx = session.ctx
+    spec_local = np.ascontiguousarray(spec_local, np.float32)
+    d, d_out = ctx.dev_malloc(spec_local.nbytes), ctx.dev_malloc(session.n_samples * 4)
+    ctx.h2d(d, spec_local)
+    ctx.check(ctx.lib.gomel_ts_phase_run_nccl(session.h, d, d_out))
+    out = np.empty(session.n_samples, np.float32)
+    ctx.d2h(out, d_out)
+    ctx.dev_free(d)
+    ctx.dev_free(d_out)
+    return out
+
+
 def run(session, iters, exchange, overlap=True):
     """All Griffin-Lim iterations of one rank.  overlap=True launches the boundary tiles first, the
     exchange on the communication stream, and the interior tiles concurrently with it."""

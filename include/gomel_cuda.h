@@ -222,6 +222,18 @@ int  gomel_nccl_unique_id(gomel_ctx *ctx, char id_out[128]);
 int  gomel_ts_nccl_init(gomel_ts *ts, const char id[128]);
 int  gomel_ts_run_nccl(gomel_ts *ts, int first_iter, int n_iters, int overlap);
 
+/* phase.ISTFT (phase/phase.go:93-133) of one long clip split by time over the same sessions (cfg.n_freqs,
+ * cfg.volume_boost; uniform tiles): every rank inverts its own frames (gomel_ts_phase_istft; d_spec_local:
+ * [n_frames_local][n_freqs][2] float32), ONE partial of 2816 floats per rank boundary travels from the earlier
+ * rank's tail (send_tail) into the later rank's head region (recv_tail) -- by the caller on the communication stream
+ * between gomel_ts_comm_begin / gomel_ts_comm_end, or by gomel_ts_phase_run_nccl -- and gomel_ts_phase_finish adds
+ * it and applies the window-sum gain, a function of the GLOBAL sample index (max of the window sum in closed form
+ * from host tables).  d_out_local: n_samples_local floats; samples [0, n_frames_local*Window) are this rank's. */
+int  gomel_ts_phase_istft(gomel_ts *ts, const float *d_spec_local);
+int  gomel_ts_phase_halo_ptrs(gomel_ts *ts, float **send_tail, float **recv_tail);
+int  gomel_ts_phase_finish(gomel_ts *ts, float *d_out_local);
+int  gomel_ts_phase_run_nccl(gomel_ts *ts, const float *d_spec_local, float *d_out_local);
+
 /* ---- pipelined host batch (end-to-end: pinned host float32 in, float32 out, H2D/compute/D2H
  * overlapped chunk by chunk on three streams).  mel: [n_clips][n_frames*n_mels*2],
  * init: [n_clips][ola_len] or NULL, out: [n_clips][ola_len]. */

@@ -431,6 +431,28 @@ def test_timesplit_short_boundary_tiles(mctx, lib, oracle, world, tile, edge, it
     assert rel_l2(split, ref) < TOL_GL
 
 
+@pytest.mark.parametrize("world,seconds,tile,num_freqs,boost", [(2, 2.0, 8, 768, 0.0), (3, 3.3, 6, 768, 1.7), (4, 4.1, 4, 1536, 0.0),
+                                                                (2, 0.9, 10, 836, 0.0)])
+def test_timesplit_phase_istft_matches_single_gpu(ctx, lib, oracle, world, seconds, tile, num_freqs, boost):
+    """SURVEY 8(e) third case: phase.ISTFT (phase/phase.go:93-133) of one clip with its frames split over `world`
+    ranks -- one transfer of 2816 floats per boundary, gain from the GLOBAL sample index (fade zones only on the
+    first / last rank, max of the window sum in closed form).  Same tile size -> same partial sums -> bit-identical
+    to the unsplit call; and inside the STFT tolerance of the float64 oracle."""
+    from gomel_b200 import timesplit
+    cfg = lib.make_config(n_fft=4096, hop=1280, n_mels=0, n_freqs=num_freqs, gl_iters=0, volume_boost=boost)
+    ocfg = oracle.config(num_freqs=num_freqs, volume_boost=boost)
+    spec = oracle.to_phase(ocfg, synth_clip(52, seconds))
+    frames = len(spec) // num_freqs
+    ola = 4096 + (frames - 1) * 1280
+    split = timesplit.phase_istft_local(ctx, cfg, spec, world, tile_frames=tile)
+    ctx.set_tile_frames(tile)
+    whole = ctx.from_phase(cfg, spec.astype(np.float32).astype(np.float64))
+    ctx.set_tile_frames(0)
+    assert split.shape == (ola,)
+    assert np.array_equal(split, whole.astype(np.float32))
+    assert rel_l2(split, oracle.from_phase(ocfg, spec)) < TOL_STFT
+
+
 def test_timesplit_real_nccl_when_two_gpus():
     """the NCCL halo exchange itself needs >= 2 GPUs (gpurun --gpus 2); on one GPU the multi-rank
     path is covered by test_timesplit_emulated_ranks_match_single_gpu"""
