@@ -240,3 +240,87 @@ func (x *Ctx) Image(buf [][2]float64, mels int) ([]uint16, error) {
 		(*C.ushort)(unsafe.Pointer(&out[0])), nil)
 	return out, x.err(rc)
 }
+
+// ToMelBatch runs gomel_to_mel_batch_host on clips of any lengths: ToMel frames depend only on local samples, so
+// every clip is zero-extended to the longest one and only its own frames are kept (float32 across the boundary).
+func ToMelBatch(cfg Config, fmin, fmax float64, clips [][]float64) ([][][2]float64, error) {
+	x, err := Default()
+	if err != nil {
+		return nil, err
+	}
+	if err := x.SetMelTables(cfg, fmin, fmax); err != nil {
+		return nil, err
+	}
+	cfg.MelFmin, cfg.MelFmax = fmin, fmax
+	nmax := 0
+	for _, c := range clips {
+		if len(c) > nmax {
+			nmax = len(c)
+		}
+	}
+	if nmax == 0 {
+		return nil, errors.New("gomel: no samples")
+	}
+	_, frMax, _, err := Frames(cfg, nmax)
+	if err != nil {
+		return nil, err
+	}
+	wav := make([]float32, len(clips)*nmax)
+	for i, c := range clips {
+		for j, v := range c {
+			wav[i*nmax+j] = float32(v)
+		}
+	}
+	per := frMax * cfg.NMels * 2
+	out := make([]float32, len(clips)*per)
+	cc := cfg.c()
+	if e := x.err(C.gomel_to_mel_batch_host(x.h, &cc, (*C.float)(unsafe.Pointer(&wav[0])), C.int(len(clips)), C.long(nmax),
+		(*C.float)(unsafe.Pointer(&out[0])), 0)); e != nil {
+		return nil, e
+	}
+	res := make([][][2]float64, len(clips))
+	for i, c := range clips {
+		_, fr, _, _ := Frames(cfg, len(c))
+		spec := make([][2]float64, fr*cfg.NMels)
+		for k := range spec {
+			spec[k] = [2]float64{float64(out[i*per+2*k]), float64(out[i*per+2*k+1])}
+		}
+		res[i] = spec
+	}
+	return res, nil
+}
+
+// FromMelBatchPCM16 runs gomel_from_mel_batch_host_pcm16 on spectrograms that all have `frames` frames; the start
+// signals are drawn on the device (U[0,1), seeded).  Returns the 16-bit samples dumpwav would write.
+func FromMelBatchPCM16(cfg Config, fmin, fmax float64, specs [][][2]float64, frames int) ([][]int16, error) {
+	x, err := Default()
+	if err != nil {
+		return nil, err
+	}
+	if err := x.SetMelTables(cfg, fmin, fmax); err != nil {
+		return nil, err
+	}
+	cfg.MelFmin, cfg.MelFmax = fmin, fmax
+	per := frames * cfg.NMels * 2
+	mel := make([]float32, len(specs)*per)
+	for i, s := range specs {
+		if len(s) != frames*cfg.NMels {
+			return nil, errors.New("gomel: spectrogram length != frames * NumMels")
+		}
+		for k, e := range s {
+			mel[i*per+2*k], mel[i*per+2*k+1] = float32(e[0]), float32(e[1])
+		}
+	}
+	ola := cfg.NFFT + (frames-1)*cfg.Hop
+	pcm := make([]int16, len(specs)*ola)
+	cc := cfg.c()
+	if e := x.err(C.gomel_from_mel_batch_host_pcm16(x.h, &cc, (*C.float)(unsafe.Pointer(&mel[0])), C.int(len(specs)),
+		C.long(frames), nil, 0, (*C.short)(unsafe.Pointer(&pcm[0])), 0)); e != nil {
+		return nil, e
+	}
+	res := make([][]int16, len(specs))
+	for i := range specs {
+		res[i] = pcm[i*ola : (i+1)*ola]
+	}
+	return res, nil
+}

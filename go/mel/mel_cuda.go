@@ -11,6 +11,25 @@ import (
 	"github.com/neurlang/gomel/internal/gomelcuda"
 )
 
+// CudaConfig / LoadWavRate / LoadFlacRate / LoadPng / DumpImage / IsPadded export what cmd/gomelbatch needs of the
+// package's private helpers (mel/impl.go); DumpWavPCM16 is dumpwav (mel/impl.go:195-232) for samples the GPU has
+// already quantised (gomel_from_mel_batch_host_pcm16).
+func (m *Mel) CudaConfig() gomelcuda.Config                 { return m.cudaConfig() }
+func LoadWavRate(name string) ([]float64, float64)          { return loadwav(name) }
+func LoadFlacRate(name string) ([]float64, float64)         { return loadflac(name) }
+func LoadPng(name string, reverse bool) ([][2]float64, float64, float64) { return loadpng(name, reverse) }
+func IsPadded(originalLen, paddedLen, filter int) bool      { return isPadded(originalLen, paddedLen, filter) }
+func DumpImage(name string, buf [][2]float64, mels int, reverse bool, samplesInMel, sr float64) error {
+	return dumpimage(name, buf, mels, reverse, samplesInMel, sr)
+}
+func DumpWavPCM16(name string, pcm []int16, sr int) error {
+	data := make([]float64, len(pcm))
+	for i, v := range pcm {
+		data[i] = float64(v) / 32767.0 // beep re-quantises with int16(v * 32767): exact for every int16
+	}
+	return dumpwav(name, data, sr)
+}
+
 func (m *Mel) cudaConfig() gomelcuda.Config {
 	return gomelcuda.Config{NFFT: m.Resolut, Hop: m.Window, NMels: m.NumMels, GLIters: m.GriffinLimIterations,
 		TuneMul: m.TuneMul, TuneAdd: m.TuneAdd, VolumeBoost: m.VolumeBoost, MelFmin: m.MelFmin, MelFmax: m.MelFmax}

@@ -22,6 +22,14 @@ def _mel():
     return m
 
 
+def _phase():
+    from .phase import NewPhase
+    p = NewPhase()                       # cmd/tophase/main.go:24-27: NumFreqs 768 * 2, YReverse
+    p.y_reverse = True
+    p.num_freqs = 768 * 2
+    return p
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) < 2:
@@ -29,9 +37,11 @@ def main(argv=None):
         return 1
     tool, name = argv[0], argv[1]
     try:
-        if tool == "tomel":
-            src = name if name.endswith(".wav") else name + ".wav"
-            _mel().ToMelWav(src, name + ".png" if name.endswith(".wav") else name + ".png")
+        if tool == "tomel":                      # cmd/tomel/main.go:33-59: .flac -> ToMelFlac, .wav -> ToMelWav, else + ".wav"
+            if name.endswith(".flac"):
+                _mel().ToMelFlac(name, name + ".png")
+            else:
+                _mel().ToMelWav(name if name.endswith(".wav") else name + ".wav", name + ".png")
         elif tool == "towav":
             m = _mel()
             if len(argv) > 2:
@@ -43,10 +53,14 @@ def main(argv=None):
         elif tool == "towav-dir":
             from . import batch
             print("\n".join(batch.towav_dir(name, argv[2], _mel())))
-        elif tool == "tophase":
-            Phase().to_phase_wav(name, name + ".png")
-        elif tool == "fromphase":
-            Phase().to_wav_png(name, name + ".wav")
+        elif tool == "tophase":                  # cmd/tophase/main.go:29-55 (Go names, Go codec flavour)
+            p = _phase()
+            if name.endswith(".flac"):
+                p.ToPhaseFlac(name, name + ".png")
+            else:
+                p.ToPhaseWav(name if name.endswith(".wav") else name + ".wav", name + ".png")
+        elif tool == "fromphase":                # cmd/fromphase/main.go:20-32
+            _phase().ToWavPng(name, name + ".wav")
         else:
             print(__doc__)
             return 1

@@ -164,6 +164,21 @@ class Phase:
         buf, sr = codec.load_wav(inputFile)
         self._go_to_png(buf, sr, outputFile)
 
+    def ToWavPng(self, inputFile, outputFile):
+        """phase.ToWavPng (phase/phase.go:246-275): Go PNG flavour (16 metadata bytes, blue-channel wrap), trim only if
+        isPadded, SampleRate defaults to the family's main rate, dumpwav (truncating 16-bit PCM)"""
+        buf, samples, samplerate = codec.phase_load_png_go(inputFile, self.y_reverse, self.ihsPasses(), self.HDR,
+                                                           device=self.device)
+        if len(buf) == 0:
+            raise ErrFileNotLoaded()
+        owave = self.FromPhase(buf)
+        if int(samples) > 0 and is_padded(int(samples), len(owave), self.window) and len(owave) > int(samples):
+            owave = owave[:int(samples)]
+        main_rate = 44100 if self.num_freqs in (836, 836 * 2) else 48000
+        if samplerate != 0 and not self.sample_rate:
+            self.sample_rate = main_rate
+        codec.save_wav(outputFile, owave, self.sample_rate or 0)
+
     def FromPhase(self, ospectrum):
         """phase.FromPhase (phase/phase.go:136-153): boost applied iff != 0 (phase/phase.go:146)"""
         return _lib.default_context(self.device).from_phase(self._cfg(self.volume_boost), ospectrum)
