@@ -419,20 +419,26 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
     const long n_sig = (long)n_clips * sig_stride;
     const size_t sig_bytes = (size_t)n_sig * 4;
     const bool fill = !io.init32 && !io.init64;
-    if (int rc = gl_reserve(ctx, cfg, n_clips, n_frames, sig_stride, fill)) return rc;
+    if (int rc = gl_reserve(ctx, cfg, n_clips, n_frames, sig_stride, fill && lead_iters(ctx, cfg, geo) == 0)) return rc;
     const float* init32 = io.init32;
-    if (fill) {
+    const double* init64 = io.init64;
+    if (fill && lead > 0) {         // the float64 lead iterations read their start signal as doubles: draw it as such
+        double* b = (double*)ctx->scratch[S_LSIGA];
+        k_fill_uniform<double><<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(b, n_sig, seed);
+        ctx->launches++;
+        init64 = b;
+    } else if (fill) {
         float* b = (float*)ctx->scratch[S_INIT];
-        k_fill_uniform<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(b, n_sig, seed);
+        k_fill_uniform<float><<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(b, n_sig, seed);
         ctx->launches++;
         init32 = b;
     }
     ctx->hot_launches = 0; ctx->lead_launches = 0;
     if (iters == 0) {       // mel/mel.go:85: zero iterations return the start signal
         if (io.out64) {
-            if (io.init64) CU(cudaMemcpyAsync(io.out64, io.init64, (size_t)n_sig * 8, cudaMemcpyDeviceToDevice, ctx->st));
+            if (init64) CU(cudaMemcpyAsync(io.out64, init64, (size_t)n_sig * 8, cudaMemcpyDeviceToDevice, ctx->st));
             else { k_f32_to_f64<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(init32, io.out64, n_sig, 1.0); ctx->launches++; }
-        } else if (io.init64) { d64::k_f64_to_f32<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(io.init64, io.out32, n_sig); ctx->launches++; }
+        } else if (init64) { d64::k_f64_to_f32<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(init64, io.out32, n_sig); ctx->launches++; }
         else CU(cudaMemcpyAsync(io.out32, init32, sig_bytes, cudaMemcpyDeviceToDevice, ctx->st));
         return 0;
     }
@@ -467,8 +473,8 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
     if (lead > 0) {
         double* sg[2] = { (double*)ctx->scratch[S_LSIGA], (double*)ctx->scratch[S_LSIGB] };
         double* hb[2] = { (double*)ctx->scratch[S_LHB0], (double*)ctx->scratch[S_LHB1] };
-        const double* cur = io.init64;
-        int w = 0;                                  // next buffer to write
+        const double* cur = init64;
+        int w = (cur == sg[0]) ? 1 : 0;             // next buffer to write (a drawn start signal sits in sg[0])
         if (!cur) {
             k_f32_to_f64<<<grid_1d(n_sig, 256), 256, 0, ctx->st>>>(init32, sg[0], n_sig, 1.0);
             ctx->launches++;
@@ -712,7 +718,7 @@ int from_mel_f64(gomel_ctx* ctx, const gomel_config* cfg, const double* d_mel, l
     else {
         void* tmp;
         if (int rc = ensure(ctx, S_F32A, (size_t)ola * 4, &tmp)) return rc;
-        k_fill_uniform<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((float*)tmp, ola, seed);
+        k_fill_uniform<float><<<grid_1d(ola, 256), 256, 0, ctx->st>>>((float*)tmp, ola, seed);
         k_f32_to_f64<<<grid_1d(ola, 256), 256, 0, ctx->st>>>((const float*)tmp, (double*)sigA, ola, 1.0);
         ctx->launches += 2;
     }
@@ -1357,7 +1363,7 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         if (!rc && !init) {
             // indexed by the sample's position in the whole batch: the start signals do not depend on the chunking
             // and equal those of gomel_from_mel_dev(seed) on the same batch
-            k_fill_uniform<<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st_pre>>>((float*)dinit[b], (long)nc * ola, seed,
+            k_fill_uniform<float><<<grid_1d((long)nc * ola, 256), 256, 0, ctx->st_pre>>>((float*)dinit[b], (long)nc * ola, seed,
                                                                                  (long)c0 * ola);
             ctx->launches++;
         }
@@ -1587,7 +1593,7 @@ int gomel_ts_load(gomel_ts* ts, const float* d_mel_local, const float* d_init_lo
     if (ts->lead > 0) { if (int rc = mags_dev<float, double>(ctx, &ts->cfg, d_mel_local, ts->n_local, ts->mags64)) return rc; }
     if (d_init_local) CU(cudaMemcpyAsync(ts->sig[0], d_init_local, (size_t)ts->n_samples * 4, cudaMemcpyDeviceToDevice, ctx->st));
     else {
-        k_fill_uniform<<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(ts->sig[0], ts->n_samples, seed, ts->sample_begin);
+        k_fill_uniform<float><<<grid_1d(ts->n_samples, 256), 256, 0, ctx->st>>>(ts->sig[0], ts->n_samples, seed, ts->sample_begin);
         ctx->launches++;
     }
     if (ts->lead > 0) {       // the float64 iterations start from the exact float32 start signal

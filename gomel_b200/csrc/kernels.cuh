@@ -89,7 +89,8 @@ __global__ void k_f32_to_pcm16(const float* __restrict__ in, short* __restrict__
 }
 // counter-based U[0,1) fill for the Griffin-Lim start signal when the caller injects none
 // (mel/mel.go:80-83 draws rand.Float64(); same distribution, not bit-compatible with math/rand)
-__global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long long seed, long index_offset = 0)
+template <typename T>
+__global__ void k_fill_uniform(T* __restrict__ out, long n, unsigned long long seed, long index_offset = 0)
 {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long step = (long)gridDim.x * blockDim.x;
@@ -98,7 +99,7 @@ __global__ void k_fill_uniform(float* __restrict__ out, long n, unsigned long lo
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
-        out[i] = (float)(z >> 40) * (1.0f / 16777216.0f);
+        out[i] = (T)((float)(z >> 40) * (1.0f / 16777216.0f));       // 24-bit grid: the same value as float or double
     }
 }
 
@@ -180,6 +181,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
     const float* __restrict__ sig = p.sig + (long)clip * p.tl.sig_stride + (long)f0 * H;
     const long lim = p.tl.sig_len - (long)f0 * H;
     const int t = L.t;
+    if (MODE == MODE_MEL) {          // the pad cells of the magnitude staging rows stay zero for the whole tile
+        float* z = reinterpret_cast<float*>(smem_raw + kSmemBytes);
+        for (int i = t; i < kStageBytes / 4; i += kThreads) z[i] = 0.0f;
+    }
 
     float raw[NR], nxt[SH];
 #pragma unroll
@@ -262,11 +267,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
             float* SB = SA + 2184;
             // staged by bin of the configured transform: FS = 8 keeps the even bins of the 4096-point core
             if (FS == 16 || (L.klow & 1) == 0) {
+                // padded cell of bin klow + 256 j: (k + (k >> 4)) is linear in j (256 j is a multiple of 16)
+                const int k0 = L.klow >> (FS == 16 ? 0 : 1), q0 = k0 + (k0 >> 4);
+                constexpr int qstep = (FS == 16) ? 272 : 136;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const int k = (L.klow + 256 * j) >> (FS == 16 ? 0 : 1), q = k + (k >> 4);
-                    SA[q] = sqrt_fast(fmaf(xa[j].x, xa[j].x, xa[j].y * xa[j].y));
-                    SB[q] = sqrt_fast(fmaf(xb[j].x, xb[j].x, xb[j].y * xb[j].y));
+                    SA[q0 + qstep * j] = sqrt_fast(fmaf(xa[j].x, xa[j].x, xa[j].y * xa[j].y));
+                    SB[q0 + qstep * j] = sqrt_fast(fmaf(xb[j].x, xb[j].x, xb[j].y * xb[j].y));
                 }
             }
             if (L.special) {
@@ -289,18 +296,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
                     t0 = s0 * (1.0f - w); t0 += s1 * w;
                     t1 = s1 * (1.0f - w); t1 += s2 * w;
                 } else if (hi > lo) {                                // w = 1 / (count + 1)
-#ifndef GOMEL_EXP_NOBAND
-                    int idx = lo + (lo >> 4);
-                    float prev = S[idx];
-                    for (int k = lo; k < hi; k++) {          // prev = S[k]; next = S[k+1]
-                        idx += ((k & 15) == 15) ? 2 : 1;
-                        const float nextv = S[idx];
-                        t0 += prev; t1 += nextv;
-                        prev = nextv;
-                    }
-#else
-                    t0 = S[lo + (lo >> 4)]; t1 = S[hi + (hi >> 4)];
-#endif
+                    // The band is a contiguous run of the padded staging row; the pad cells inside it hold zeros
+                    // (cleared once per CTA), so the run is summed without any index arithmetic.  ch1 covers the
+                    // same bins shifted by one: the run minus its first bin plus the bin after its last.
+                    int q = lo + (lo >> 4);
+                    const int qe = (hi - 1) + ((hi - 1) >> 4);
+                    const float first = S[q];
+                    float sum = first;
+#pragma unroll 4
+                    for (q++; q <= qe; q++) sum += S[q];
+                    t0 = sum;
+                    t1 = (sum - first) + S[hi + (hi >> 4)];
                     t0 *= w; t1 *= w;
                 }
                 t0 = (t0 < 1e-5f) ? 1e-5f : t0;
@@ -320,13 +326,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
         } else if (MODE == MODE_PHASE) {
             float2* SA = stg;
             float2* SB = stg + 2176;
+            {
+                // bin k = klow + 256 j -> entry e = k - 1 -> padded cell e + (e >> 4) = q0 + 272 j (arithmetic shift:
+                // klow = 0 gives q0 = -2, whose j = 0 cell -- bin 0, dropped by ToPhase -- is skipped)
+                const int e0 = L.klow - 1, q0 = e0 + (e0 >> 4);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = L.klow + 256 * j;          // bin k -> entry k-1
-                if (k >= 1) {
-                    const int e = k - 1, q = e + (e >> 4);
-                    SA[q] = make_float2(xa[j].y, xa[j].x);
-                    SB[q] = make_float2(xb[j].y, xb[j].x);
+                for (int j = 0; j < 8; j++) {
+                    if (j > 0 || e0 >= 0) {
+                        SA[q0 + 272 * j] = make_float2(xa[j].y, xa[j].x);
+                        SB[q0 + 272 * j] = make_float2(xb[j].y, xb[j].x);
+                    }
                 }
             }
             if (L.special) {
@@ -337,10 +346,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_stft_fwd(const FwdParams p)
             __syncthreads();
             float2* outp = p.phase_out + ((long)clip * p.tl.n_frames + fA) * p.n_freqs;
             const int nfq = p.n_freqs;
-            for (int o = t; o < 2 * nfq; o += kThreads) {
-                const int fr = (o >= nfq), e = o - fr * nfq;
-                if (fr == 1 && !validB) continue;
-                outp[o] = (fr ? SB : SA)[e + (e >> 4)];
+            {
+                const int qt = t + (t >> 4);                  // entry t + 256 i sits in padded cell qt + 272 i
+                for (int i = 0, e = t; e < nfq; i++, e += kThreads) outp[e] = SA[qt + 272 * i];
+                if (validB)
+                    for (int i = 0, e = t; e < nfq; i++, e += kThreads) outp[nfq + e] = SB[qt + 272 * i];
             }
         } else {
             float2* SA = stg;
@@ -921,18 +931,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_istft_phase(const SynParams p)
         // slots Z'[k] = conj(XA[N-k]) + i*conj(XB[N-k]).  The 1/N of the inverse transform lives in the gain tables.
         float2 v[16];
         {
-            const int top = nfq - 1;
+            const int top = nfq - 1, qtop = top + (top >> 4);
             const int elo = L.klow - 1;                 // entry of bin klow + 256 j          (lower slot j)
             const int ehi = 255 - L.klow;               // entry of bin 4096 - (klow + 256 j)  (upper slot j: + 256 (15 - j))
+            // padded cell of entry e0 + 256 i is q(e0) + 272 i; entries beyond the kept ones read the last kept one (grow)
+            // (arithmetic shift: elo = -1, the klow = 0 thread, gives 272 j - 2; its j = 0 value is replaced below)
+            const int qlo = elo + (elo >> 4), qhi = ehi + (ehi >> 4);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int e = min(elo + 256 * j, top), q = e + (e >> 4);
-                const float2 ea = SA[max(q, 0)], eb = SB[max(q, 0)];
+                int q = qlo + 272 * j;
+                if (j == 0) q = max(q, 0);
+                if (elo + 256 * j > top) q = qtop;
+                const float2 ea = SA[q], eb = SB[q];
                 v[j] = join_lo(make_float2(ea.y, ea.x), make_float2(eb.y, eb.x));
             }
 #pragma unroll
             for (int j = 8; j < 16; j++) {
-                const int e = min(ehi + 256 * (15 - j), top), q = e + (e >> 4);
+                const int q = (ehi + 256 * (15 - j) <= top) ? qhi + 272 * (15 - j) : qtop;
                 const float2 ea = SA[q], eb = SB[q];
                 v[j] = join_hi(make_float2(ea.y, ea.x), make_float2(eb.y, eb.x));
             }
@@ -978,6 +993,27 @@ __global__ void k_halo_fix(float* __restrict__ sig, const float* __restrict__ hb
     const float* __restrict__ h = hb + ((long)clip * hb_tiles + tile) * halo;
     const long room = tl.sig_len - s0;
     const int n = (int)(room < halo ? (room < 0 ? 0 : room) : halo);
+    // interior regions (the usual case): whole region present, 16-byte aligned, gain from the periodic table only
+    const long g0 = s0 + gp.gain_off;
+    const bool mid_only = !use_gain || (g0 >= gp.head_len && g0 + halo <= gp.total_len - gp.tail_len);
+    if (n == halo && mid_only && (halo & 3) == 0 && (hop & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(h)) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(d);
+        const float4* h4 = reinterpret_cast<const float4*>(h);
+        for (int o4 = threadIdx.x; o4 < halo / 4; o4 += blockDim.x) {
+            float4 x = d4[o4];
+            const float4 y = __ldg(h4 + o4);
+            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+            if (use_gain) {
+                int m = o4 * 4;                                   // position inside the hop period (s0 is a multiple of hop)
+                while (m >= hop) m -= hop;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gp.gain_mid + m));
+                x.x *= g.x; x.y *= g.y; x.z *= g.z; x.w *= g.w;
+            }
+            d4[o4] = x;
+        }
+        return;
+    }
     for (int o = threadIdx.x; o < n; o += blockDim.x) {
         float x = d[o] + h[o];
         if (use_gain) x *= gain_at(gp, s0 + o, o % hop);
