@@ -533,7 +533,7 @@ def run_product(args):
     # ---- the other two precision modes on the same batch, device-resident (one timed step each after one warm-up)
     modes = {}
     cfg_f64 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS, flags=_lib.FLAG_F64)
-    for name, c, prec in (("all_float32", cfg, (0, -1)), ("all_float64", cfg_f64, None)):
+    for name, c, prec in ((("all_float32", cfg, (0, -1)), ("all_float64", cfg_f64, None)) if args.modes else ()):
         prev = ctx.set_gl_precision(*prec) if prec else None
         step_device(1, c=c)
         barrier()
@@ -607,16 +607,19 @@ def run_product(args):
         if hot_n:
             per_launch_s = hot_ms / 1e3 / hot_n
             achieved = BYTES_PER_FRAME_ITER * clips * frames / per_launch_s / 1e9
-            traffic = None
+            traffic = lead_traffic = None
             tp = os.path.join(ROOT, "profiles", "gl_iter_traffic.json")
             if os.path.exists(tp):
                 try:
                     tj = json.load(open(tp))
                     traffic = tj["dram_bytes_per_frame_iter"] * clips * frames
+                    lead_traffic = tj["lead_kernel"]["dram_bytes_per_frame_iter"] * clips * frames
                 except Exception:
-                    traffic = None
+                    pass
             roofline = {"bound": "hbm", "kernel": "k_gl_iter<5, 16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame-iteration of one --set full capture "
+                                          "of this build (profiles/gl_iter_traffic.json) x the frame-iterations of one launch",
                         "algorithmic_bytes_per_launch": BYTES_PER_FRAME_ITER * clips * frames,
                         "avg_launch_ms": per_launch_s * 1e3, "launches_timed": hot_n,
                         "kernel_share_of_step": hot_ms / dev_ms,
@@ -628,7 +631,7 @@ def run_product(args):
                 l_ach = BYTES_PER_FRAME_ITER_F64 * clips * frames / l_s / 1e9
                 roofline["lead_kernel"] = {
                     "kernel": "k_gl_iter_f64<5>", "bound": "hbm nominally; FP64 pipe + shared memory in practice",
-                    "achieved": l_ach, "peak": peak, "unit": "GB/s", "frac": l_ach / peak,
+                    "achieved": l_ach, "peak": peak, "unit": "GB/s", "frac": l_ach / peak, "traffic": lead_traffic,
                     "algorithmic_bytes_per_launch": BYTES_PER_FRAME_ITER_F64 * clips * frames, "avg_launch_ms": l_s * 1e3,
                     "launches_timed": lead_n, "kernel_share_of_step": lead_ms / dev_ms,
                     "frame_iterations_per_s_per_gpu": clips * frames * lead_n / (lead_ms / 1e3)}
@@ -867,6 +870,7 @@ def main():
     ap.add_argument("--no-per-kernel", dest="per_kernel", action="store_false")
     ap.add_argument("--no-numa", dest="numa", action="store_false", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--tile", type=int, default=0, help="frames per tile (0 = library heuristic)")
+    ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the all-float32 / all-float64 comparison steps")
     ap.add_argument("--no-strong", dest="strong", action="store_false", help="skip the 1024-clips-in-total strong-scaling leg")
     ap.add_argument("--no-link", dest="link", action="store_false", help="skip the host-link ceiling probe")
     ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the parity sub-record")
