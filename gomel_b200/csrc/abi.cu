@@ -92,7 +92,6 @@ struct gomel_ctx {
     unsigned long long launches = 0;
     int tile_override = 0;
     int gl_tile_waves = 4;            // Griffin-Lim: CTA waves per iteration the automatic tiling aims at
-    int gl_stateless = 0;             // GOMEL_GL_STATELESS: float32 iterations on k_gl_iter_s (3 CTAs / SM) -- A/B knob
     std::string err;
     std::mutex mu;
 };
@@ -382,8 +381,7 @@ int gl_reserve(gomel_ctx* ctx, const gomel_config* cfg, int n_clips, long n_fram
     void* b;
     const size_t sig_bytes = (size_t)n_clips * sig_stride * 4;
     const Tiling tl = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves);
-    const Tiling tl3 = make_tiling(ctx, n_clips, n_frames, sig_stride, ola, geo.alt ? 8 : 4, ctx->gl_tile_waves, 3);
-    const size_t hb_elems = (size_t)n_clips * ((tl.n_tiles > tl3.n_tiles ? tl.n_tiles : tl3.n_tiles) + 1) * geo.halo + 4;
+    const size_t hb_elems = (size_t)n_clips * (tl.n_tiles + 1) * geo.halo + 4;
     if (need_init) { if (int rc = ensure(ctx, S_INIT, sig_bytes, &b)) return rc; }
     if (iters - lead > 0) {
         if (iters - lead > 1 || lead > 0) { if (int rc = ensure(ctx, S_SIGTMP, sig_bytes, &b)) return rc; }
@@ -400,7 +398,7 @@ int gl_reserve(gomel_ctx* ctx, const gomel_config* cfg, int n_clips, long n_fram
     return 0;
 }
 
-int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl, bool stateless,
+int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl,
                const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs);
 
 int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips, long n_frames,
@@ -510,10 +508,11 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
                 ctx->launches++;
             }
             if (conv) {
-                d64::k_f64_to_f32<<<grid_1d(nc * sig_stride, 256), 256, 0, gs[g]>>>(fin + c0 * sig_stride, conv + c0 * sig_stride, nc * sig_stride);
+                d64::k_f64_to_f32_rows<<<grid_1d(nc * ola, 256), 256, 0, gs[g]>>>(fin + c0 * sig_stride, conv + c0 * sig_stride, nc, ola, sig_stride);
                 ctx->launches++;
             } else {
-                CU(cudaMemcpyAsync(io.out64 + c0 * sig_stride, fin + c0 * sig_stride, (size_t)nc * sig_stride * 8, cudaMemcpyDeviceToDevice, gs[g]));
+                CU(cudaMemcpy2DAsync(io.out64 + c0 * sig_stride, (size_t)sig_stride * 8, fin + c0 * sig_stride, (size_t)sig_stride * 8,
+                                     (size_t)ola * 8, (size_t)nc, cudaMemcpyDeviceToDevice, gs[g]));
             }
         }
         if (int rc = join()) return rc;
@@ -522,13 +521,11 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
         cur32 = conv;
         if (iters == lead) { CU(cudaGetLastError()); return 0; }
     }
-    // ---------------- float32 iterations (a tiling of their own: the hand-over above folded every partial in)
-    const bool stateless = ctx->gl_stateless && !geo.alt;
-    const Tiling tl32 = stateless ? make_tiling(ctx, n_clips, n_frames, sig_stride, ola, 4, ctx->gl_tile_waves, 3) : tl;
-    return gl_dev_f32(ctx, cfg, geo, io, tl32, stateless, cur32, tmp, n_clips, iters, lead, ns, gs);
+    // ---------------- float32 iterations
+    return gl_dev_f32(ctx, cfg, geo, io, tl, cur32, tmp, n_clips, iters, lead, ns, gs);
 }
 
-int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl, bool stateless,
+int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl,
                const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs)
 {
     (void)cfg;
@@ -566,7 +563,6 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
             p.clip0 = c_lo(g);
             const unsigned gg = (unsigned)((long)(c_lo(g + 1) - c_lo(g)) * tl.n_tiles);
             if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
-            else if (stateless) k_gl_iter_s<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
             else k_gl_iter<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
             ctx->launches++;
         }
@@ -805,8 +801,6 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_PHASE>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_SPEC>)) return rc;
         CU(cudaFuncSetAttribute(k_gl_iter<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
-        CU(cudaFuncSetAttribute(k_gl_iter_s<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
-        if (const char* e = getenv("GOMEL_GL_STATELESS")) ctx->gl_stateless = atoi(e) != 0;
         if (int rc = set_smem_attr(ctx, k_istft_phase<kHS>)) return rc;
         return 0;
     };

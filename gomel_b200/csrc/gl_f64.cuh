@@ -457,6 +457,18 @@ __global__ void k_halo_fix_f64(double* __restrict__ sig, const double* __restric
     for (int o = threadIdx.x; o < n; o += blockDim.x) d[o] += h[o];
 }
 
+// rows of `len` valid samples, `stride` apart in both buffers: the gap after each row is not touched
+__global__ void k_f64_to_f32_rows(const double* __restrict__ in, float* __restrict__ out, long n_rows, long len, long stride)
+{
+    const long n = n_rows * len;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long step = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        const long r = i / len, o = r * stride + (i - r * len);
+        out[o] = (float)in[o];
+    }
+}
+
 __global__ void k_f64_to_f32(const double* __restrict__ in, float* __restrict__ out, long n)
 {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -669,170 +669,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     for (int j = 0; j < KEEP; j++) st(npairs * 2 * H + j * 256, acc[j]);
 }
 
-// ------------------------------------------------------------------ K5, stateless form (3 CTAs / SM)
-// Same iteration as k_gl_iter, organised like the float64 kernel (gl_f64.cuh): nothing but the transform lives in
-// registers across pairs.  A pair's 21 input rows are loaded per pair (the 2.1x re-read hits L2; the next pair's new
-// rows are prefetched into L2 one pair ahead) and the overlap-add is carried through the output buffer -- first
-// touch of a row is a plain store, later contributions are fire-and-forget RED.ADD.F32 (one thread of one CTA per
-// address, ascending frame order: deterministic).  <= 80 registers and 70 KB shared memory -> 3 CTAs (24 warps) per
-// SM, so the exchange / barrier phases of one CTA are covered by two others instead of one.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int HS>
-__global__ void __launch_bounds__(kThreads, 3) k_gl_iter_s(const SynParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve_smem(smem_raw);
-    float* const smag = reinterpret_cast<float*>(smem_raw + kSmemBytes);                 // [2][kMagStride]
-    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + kSmemBytes + kGlMagBytes);
-    float2* const zsc = reinterpret_cast<float2*>(smem_raw + kSmemBytes + kGlMagBytes + 16);   // [2][16]
-    const Lanes L = make_lanes();
-    load_tables(s, p.tables, L.t);
-    constexpr int NR = 16 + HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
-    int tile, clip;
-    if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
-    else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = p.clip0 + blockIdx.x / p.tiles_in_launch; }
-    const int f0 = tile_begin(p.tl, tile);
-    const int nf = tile_begin(p.tl, tile + 1) - f0;
-    const int npairs = (nf + 1) >> 1;
-    const int tile_len = nf * H;
-    const long sbase = (long)f0 * H;
-    const float* __restrict__ sin_ = p.sig_in + (long)clip * p.tl.sig_stride + sbase;
-    float* __restrict__ sout = p.sig_out + (long)clip * p.tl.sig_stride + sbase;
-    const long lim_l = p.tl.sig_len - sbase;
-    const int lim = (int)(lim_l < 0x7fffff00L ? lim_l : 0x7fffff00L);
-    const bool has_prev = tile > 0 || p.ext_prev, has_next = (tile + 1) < p.tl.n_tiles || p.ext_next;
-    const float* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)clip * p.hb_tiles + tile) * HALO : nullptr;
-    const float* __restrict__ hin_next = hin_own ? hin_own + HALO : nullptr;
-    float* __restrict__ hout = p.hb_out + ((long)clip * p.hb_tiles + tile) * HALO;
-    const int t = L.t;
-
-    auto ld = [&](int row) -> float {
-        const int o = row + t;
-        float x = (o < lim) ? __ldg(sin_ + o) : 0.0f;
-        if (hin_own) {
-            if (has_prev && row < HALO) x += __ldg(hin_own + o);
-            else if (has_next && row >= tile_len) x += __ldg(hin_next + (o - tile_len));
-        }
-        return x;
-    };
-    auto plain_rows = [&](int row0, int n) -> bool {
-        const int end = row0 + n * 256;
-        return end <= lim && (!has_prev || row0 >= HALO) && (!(has_next && hin_own) || end <= tile_len);
-    };
-
-    if (t == 0) mbar_init(bar, 1);
-    const int idx_lo = mag_pos(L.klow);
-    const float* __restrict__ mrow = p.mags + ((long)clip * p.tl.n_frames + f0) * kMagStride;
-    __syncthreads();                // tables + mbarrier init visible
-
-    for (int pr = 0; pr < npairs; pr++) {
-        const int off0 = pr * 2 * H;
-        const bool validB = (f0 + 2 * pr + 1) < p.tl.n_frames;
-        if (t == 0) {               // (the buffer was last read in the previous pair's substitution stage, >= 2 barriers ago)
-            const unsigned bytes = validB ? (unsigned)kGlMagBytes : (unsigned)(kMagStride * 4);
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(smag, mrow + (long)(2 * pr) * kMagStride, bytes, bar);
-        }
-        float2 v[16];
-        {
-            float raw[NR];
-            if (plain_rows(off0, NR)) {
-#pragma unroll
-                for (int j = 0; j < NR; j++) raw[j] = __ldg(sin_ + off0 + j * 256 + t);
-            } else {
-#pragma unroll
-                for (int j = 0; j < NR; j++) raw[j] = ld(off0 + j * 256);
-            }
-#pragma unroll
-            for (int m = 0; m < 16; m++) { const float w = win_at(s.win, m, t); v[m] = make_float2(raw[m] * w, raw[m + HS] * w); }
-        }
-        if (pr + 1 < npairs) {      // pull the next pair's new signal rows towards L2 while this pair computes
-            const int r0 = off0 + 2 * H + KEEP * 256 + t;
-#pragma unroll
-            for (int j = 0; j < 2 * HS; j++) if (r0 + j * 256 < lim) prefetch_l2(sin_ + r0 + j * 256);
-        }
-
-        fft4096_fwd(v, s, L);
-
-        mbar_wait(bar, (unsigned)(pr & 1));
-        {
-            const float* __restrict__ mA = smag + idx_lo;
-            const float* __restrict__ mB = smag + kMagStride + idx_lo;
-            const bool w0 = (t >> 5) == 0;
-            if (w0) {
-                if (L.special) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) zsc[i] = v[i];
-                }
-                __syncwarp();
-            }
-            float2 nlo[8], nhi[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float ma = mA[j * 256];
-                const float mb = validB ? mB[j * 256] : 0.0f;
-                const float2 P = shfl2(v[15 - j], L.src);
-                const float2 z = v[j];
-                const float2 ya = subst_phase(split_a(z, P), ma);
-                const float2 yb = subst_phase(split_b(z, P), mb);
-                nlo[j] = join_lo(ya, yb);
-                nhi[j] = shfl2(join_hi(ya, yb), L.src);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) { v[j] = nlo[j]; v[15 - j] = nhi[j]; }
-            if (w0) {
-                const int j = t - 1;                                   // lanes 1..9 -> special pair j = 0..8
-                if (j >= 0 && j <= 8) {
-                    const int jp = (16 - j) & 15, mi = (j == 8) ? 2048 : j * 256;
-                    const float ma = smag[mi];
-                    const float mb = validB ? smag[kMagStride + mi] : 0.0f;
-                    const float2 z = zsc[j], P = zsc[jp];
-                    const float2 ya = subst_phase(split_a(z, P), ma);
-                    const float2 yb = subst_phase(split_b(z, P), mb);
-                    zsc[16 + j] = join_lo(ya, yb);
-                    if (jp != j) zsc[16 + jp] = join_hi(ya, yb);
-                }
-                __syncwarp();
-                if (L.special) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = zsc[16 + i];
-                }
-            }
-        }
-
-        fft4096_inv(v, s, L);
-
-        // windowed overlap-add through the output buffer: row r of the pair's 21-row span receives frame A's sample r
-        // (r < 16) and frame B's sample r - HS (r >= HS); rows 0..KEEP-1 were first written by this tile's previous pair
-        {
-            float o[NR];
-#pragma unroll
-            for (int m = 0; m < 16; m++) o[m] = v[m].x * win_at(s.win, m, t);
-#pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const float w = win_at(s.win, m, t);
-                o[m + HS] = (m + HS < 16) ? fmaf(v[m].y, w, o[m + HS]) : v[m].y * w;
-            }
-            const bool fast = off0 + NR * 256 <= lim && (!has_prev || off0 >= HALO);
-            if (fast && pr > 0) {
-#pragma unroll
-                for (int r = 0; r < KEEP; r++) atomicAdd(sout + off0 + r * 256 + t, o[r]);
-#pragma unroll
-                for (int r = KEEP; r < NR; r++) sout[off0 + r * 256 + t] = o[r];
-            } else {
-#pragma unroll
-                for (int r = 0; r < NR; r++) {
-                    const int row = off0 + r * 256, ofs = row + t;
-                    if (ofs >= lim) continue;
-                    float* dst = (has_prev && row < HALO) ? hout + ofs : sout + ofs;
-                    if (pr == 0 || r >= KEEP) *dst = o[r];
-                    else atomicAdd(dst, o[r]);
-                }
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------ K4+K6: phase ISTFT
 // Replaces grow + Phase.undospectrum + phase.ISTFT + the VolumeBoost loop of phase.FromPhase

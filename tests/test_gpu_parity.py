@@ -386,6 +386,62 @@ def test_launch_counter_counts_kernels(mctx, lib, oracle):
     assert mctx.launch_count() > before
 
 
+def test_kernels_stay_inside_their_buffers(mctx, lib, oracle):
+    """compute-sanitizer is closed on this GPU pool, so the bounds are checked by canaries: every output buffer is
+    allocated with guard zones (and the signal rows with a gap between ola_len and sig_stride) pre-filled with a
+    bit pattern that no kernel may change -- float64 lead iterations, float32 iterations, RED accumulation, halo
+    fix-ups, phase ISTFT, forward kernels; odd frame counts and several tilings."""
+    guard = 4096
+    pat = np.float32(-7.25e33)
+
+    def guarded(n_payload):
+        buf = np.full(n_payload + 2 * guard, pat, np.float32)
+        d = mctx.dev_malloc(buf.nbytes)
+        mctx.h2d(d, buf)
+        return d, C.c_void_p(d.value + guard * 4)
+
+    def check(d, n_payload, holes=()):
+        back = np.empty(n_payload + 2 * guard, np.float32)
+        mctx.d2h(back, d)
+        assert np.all(back[:guard] == pat) and np.all(back[guard + n_payload:] == pat), "guard zone overwritten"
+        for a, b in holes:
+            assert np.all(back[guard + a:guard + b] == pat), "gap between ola_len and sig_stride overwritten"
+        mctx.dev_free(d)
+        return back[guard:guard + n_payload]
+
+    n_clips = 3
+    for seconds, iters, tile in ((0.75, 6, 0), (0.61, 3, 4), (1.3, 9, 6)):
+        cfg = mel_cfg(lib, iters=iters)
+        wavs = np.stack([synth_clip(70 + c, seconds) for c in range(n_clips)]).astype(np.float32)
+        n = wavs.shape[1]
+        npad, frames, ola = lib.frames(cfg, n)
+        stride = ola + 96                                       # a gap after every clip's signal
+        in_stride = (npad + 3) & ~3
+        sig = np.zeros((n_clips, in_stride), np.float32)
+        sig[:, :n] = wavs
+        d_sig = mctx.dev_malloc(sig.nbytes)
+        mctx.h2d(d_sig, sig)
+        mctx.set_tile_frames(tile)
+        d_mel_raw, d_mel = guarded(n_clips * frames * 192 * 2)
+        mctx.check(mctx.lib.gomel_to_mel_dev(mctx.h, C.byref(cfg), d_sig, n_clips, in_stride, npad, frames, d_mel))
+        d_out_raw, d_out = guarded(n_clips * stride)
+        mctx.check(mctx.lib.gomel_from_mel_dev(mctx.h, C.byref(cfg), d_mel, n_clips, frames, None, 5, stride, d_out))
+        mctx.sync()
+        out = check(d_out_raw, n_clips * stride, [(c * stride + ola, (c + 1) * stride) for c in range(n_clips)])
+        assert np.isfinite(out.reshape(n_clips, stride)[:, :ola]).all()
+        mel = check(d_mel_raw, n_clips * frames * 192 * 2)
+        assert np.isfinite(mel).all()
+        d_ph_raw, d_ph = guarded(n_clips * frames * 768 * 2)
+        mctx.check(mctx.lib.gomel_to_phase_dev(mctx.h, C.byref(cfg), d_sig, n_clips, in_stride, npad, frames, d_ph))
+        d_w_raw, d_w = guarded(n_clips * stride)
+        mctx.check(mctx.lib.gomel_from_phase_dev(mctx.h, C.byref(cfg), d_ph, n_clips, frames, stride, d_w))
+        mctx.sync()
+        check(d_w_raw, n_clips * stride, [(c * stride + ola, (c + 1) * stride) for c in range(n_clips)])
+        check(d_ph_raw, n_clips * frames * 768 * 2)
+        mctx.set_tile_frames(0)
+        mctx.dev_free(d_sig)
+
+
 # ------------------------------------------------------------------ time-split (config 5) on one GPU
 @pytest.mark.parametrize("world,overlap,seconds,iters", [(2, False, 2.0, 3), (3, True, 2.0, 4), (4, True, 3.1, 2),
                                                          (2, True, 2.0, 7), (3, False, 2.6, 6), (4, True, 3.1, 9)])
