@@ -49,6 +49,9 @@ struct Mel {                                         // mel/mel.go:10-27
     int SampleRate = 0;
     // extension: start-signal injection for parity runs (empty = draw U[0,1) like math/rand)
     std::vector<double> InitSignal;
+    // extension: GOMEL_FLAG_F64 -- every Griffin-Lim iteration in float64 (default: the library's precision policy,
+    // max(4, iterations - 28) float64 lead iterations, then float32)
+    bool Float64 = false;
 
     gomel_config config() const
     {
@@ -56,6 +59,7 @@ struct Mel {                                         // mel/mel.go:10-27
         c.n_fft = Resolut; c.hop = Window; c.n_mels = NumMels; c.gl_iters = GriffinLimIterations;
         c.tune_mul = TuneMul; c.tune_add = TuneAdd; c.volume_boost = VolumeBoost;
         c.mel_fmin = MelFmin; c.mel_fmax = MelFmax;        // key of this object's filterbank tables
+        c.flags = Float64 ? GOMEL_FLAG_F64 : 0;
         return c;
     }
 

@@ -111,6 +111,91 @@ def test_two_rank_gloo_sharding_and_halo_protocol():
     assert err < 1e-12          # the split is exact up to float64 rounding of two-term sums
 
 
+def _phase_worker(rank, world, port, q):
+    """phase.ISTFT of one clip split by time (third case) as a NumPy rank model over gloo: every rank
+    inverts its own frames, ONE partial of 2816 samples per boundary travels tail -> next rank, the owner adds it and
+    applies the window-sum gain indexed by the GLOBAL sample position (phase/phase.go:93-133)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gomel_b200 import timesplit
+        from oracle import oracle_np as ONP
+        from util import synth_clip
+        N, H, HALO, nfq = 4096, 1280, 4096 - 1280, 768
+        spec = ONP.to_phase(synth_clip(12, 2.2), nfq)
+        frames = len(spec) // nfq
+        ola = N + (frames - 1) * H
+        fb, nf = timesplit.partition(frames, world, tile_frames=6)[rank]
+        s = spec.reshape(frames, nfq, 2)[fb:fb + nf]
+        X = np.zeros((nf, N // 2 + 1), np.complex128)
+        X[:, 1:nfq + 1] = s[:, :, 1] + 1j * s[:, :, 0]
+        X[:, nfq + 1:] = X[:, nfq:nfq + 1]
+        X[:, N // 2] = X[:, N // 2].real
+        w = np.hanning(N)
+        y = np.fft.irfft(X, n=N, axis=1) * w
+        local = np.zeros(nf * H + HALO)
+        for f in range(nf):
+            local[f * H:f * H + N] += y[f]
+        reqs = []
+        recv = torch.zeros(HALO, dtype=torch.float64)
+        if rank + 1 < world:
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(local[nf * H:])), rank + 1))
+        if rank > 0:
+            reqs.append(dist.irecv(recv, rank - 1))
+        for r in reqs:
+            r.wait()
+        if rank > 0:
+            local[:HALO] += recv.numpy()
+        # window-sum gain from the GLOBAL position: data independent, every rank rebuilds it from the frame count
+        ws = np.zeros(ola)
+        for f in range(frames):
+            ws[f * H:f * H + N] += w * w
+        thr = ws.max() * 0.5
+        g = ws[fb * H:fb * H + len(local)]
+        out = local.copy()
+        hi, mid = g > thr, (g <= thr) & (g > 1e-21)
+        out[hi] /= g[hi]
+        out[mid] = out[mid] / g[mid] * (g[mid] / thr)
+        own = out[:nf * H + (HALO if rank == world - 1 else 0)]
+        mine = torch.from_numpy(np.ascontiguousarray(own))
+        lens = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(lens, torch.tensor([len(mine)], dtype=torch.int64))
+        if rank == 0:
+            pieces = [mine.numpy()]
+            for r in range(1, world):
+                buf = torch.zeros(int(lens[r]), dtype=torch.float64)
+                dist.recv(buf, r)
+                pieces.append(buf.numpy())
+            stitched = np.concatenate(pieces)
+            ref = ONP.from_phase(spec, nfq)
+            q.put(("ok", float(np.linalg.norm(stitched - ref) / np.linalg.norm(ref)), len(stitched), ola))
+        else:
+            dist.send(mine, 0)
+    except Exception as e:      # noqa: BLE001
+        q.put(("fail", repr(e), 0, 0))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_phase_istft_single_exchange():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_phase_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    status, err, n, ola = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    assert status == "ok", err
+    assert n == ola and err < 1e-12
+
+
 def test_partition_properties():
     from gomel_b200 import shard, timesplit
     for frames, world, T in ((124029, 8, 16), (342, 2, 8), (342, 8, 16), (1000, 3, 54)):
