@@ -207,3 +207,78 @@ def test_batch_directory_tools_match_single_file_api(tmp_path, oracle, ctx):
         x, _ = codec.load_wav(str(wavd / f"{name}.wav.png.wav"))
         y, _ = codec.load_wav(str(tmp_path / "single.wav"))
         assert len(x) == len(y) and np.abs(x - y).max() * 32767 <= 1.001   # float32 vs float64 mel input: <= 1 PCM LSB
+
+
+# ------------------------------------------------------------------ FLAC entry points
+def _flac_fixture(path, seconds, sr, stereo, seed):
+    from gomel_b200 import flac
+    rng = np.random.default_rng(seed)
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    ch = [(9000 * np.sin(2 * np.pi * (330 + 110 * c) * t + c) + rng.normal(0, 300, n)).astype(np.int64) for c in range(2 if stereo else 1)]
+    pcm = np.stack(ch, axis=1)
+    flac.encode(path, pcm if stereo else pcm[:, 0], sr, bps=16, blocksize=4096, stereo_mode="mid_side" if stereo else "independent")
+    return pcm
+
+
+def test_tomelflac_is_tomel_of_the_go_decoded_samples(tmp_path, ctx):
+    """mel.ToMelFlac (mel/mel.go:176-192): loadflac's block-wise channel concatenation scaled by 1/65536, then ToMel and
+    dumpimage -- the PNG equals the one written from the same samples through the buffer API"""
+    from gomel_b200 import codec
+    ff, pf, qf = str(tmp_path / "s.flac"), str(tmp_path / "s.png"), str(tmp_path / "ref.png")
+    pcm = _flac_fixture(ff, 1.3, 44100, True, 3)
+    m = _mel()
+    m.ToMelFlac(ff, pf)
+    blocks = [pcm[i:i + 4096] for i in range(0, len(pcm), 4096)]
+    buf = np.concatenate([b[:, c] for b in blocks for c in range(2)]) / 65536.0
+    spec = m.ToMel(buf)
+    codec.mel_dump_image(qf, spec, 192, True, float(len(buf) * 192) / float(len(spec)), 44100.0)
+    assert np.array_equal(codec.read_png(pf), codec.read_png(qf))
+    from gomel_b200 import mel as M
+    assert np.array_equal(M.LoadFlac(ff), buf)
+    with pytest.raises(M.ErrFileNotLoaded):
+        m.ToMelFlac(str(tmp_path / "missing.flac"), pf)
+
+
+def test_python_phase_flac_entry_points(tmp_path, ctx):
+    """phase.py:255-318: to_tensor_flac == to_phase(zero-stuffed soundfile samples); to_phase_flac writes the PNG that
+    save_image writes for that spectrogram, with the sample rate following the stuffing ratio (22050 -> 44100)"""
+    from gomel_b200 import phase as P
+    ff, pf, qf = str(tmp_path / "p.flac"), str(tmp_path / "p.png"), str(tmp_path / "q.png")
+    pcm = _flac_fixture(ff, 1.0, 22050, True, 4)
+    audio = np.mean(pcm / 32768.0, axis=1)
+    ph = P.Phase()
+    spec = ph.to_tensor_flac(ff)
+    assert ph.num_freqs == 836 and ph.family is False
+    up = P.zero_stuff_upsample(audio, 1, 1)
+    want = P.Phase(sample_rate=22050).to_phase(up)
+    assert spec.shape == want.shape and np.array_equal(spec, want)
+    ph2 = P.Phase()
+    ph2.to_phase_flac(ff, pf)
+    P.save_image(qf, want, 836, float(len(up) * 836) / float(len(want)), 44100, True, False, 0)
+    assert np.array_equal(P.codec.read_png(pf), P.codec.read_png(qf))
+    back, samples, rate, nfq = P.load_image(pf, True, False, 0)
+    assert nfq == 836 and abs(rate - 44100) < 64 and back.shape == want.shape
+
+
+def test_go_phase_flac_and_wav_tools_round_trip(tmp_path, ctx, oracle):
+    """cmd/tophase + cmd/fromphase on the Go names: ToPhaseFlac (1/32768, length before stuffing in the metadata),
+    ToWavPng (trim only if isPadded, family main rate, truncating 16-bit writer)"""
+    from gomel_b200 import codec
+    from gomel_b200.cli import _phase
+    ff, pf, wf = str(tmp_path / "g.flac"), str(tmp_path / "g.png"), str(tmp_path / "g.wav")
+    pcm = _flac_fixture(ff, 1.1, 48000, False, 5)
+    p = _phase()
+    p.ToPhaseFlac(ff, pf)
+    buf, samples, sr = codec.phase_load_png_go(pf, True, p.ihsPasses(), p.HDR)
+    frames = len(buf) // p.num_freqs
+    assert abs(samples / frames * frames - len(pcm)) < 0.002 * len(pcm) and abs(sr - 48000) < 64     # float16 metadata
+    q = _phase()
+    q.ToWavPng(pf, wf)
+    assert q.sample_rate == 48000
+    got, got_sr = codec.load_wav(wf)
+    assert got_sr == 48000.0
+    ref = oracle.from_phase(oracle.config(num_freqs=p.num_freqs), buf)
+    n = min(len(got), len(ref))
+    assert len(got) in (len(ref), int(samples))
+    assert np.abs(got[:n] * 32767.0 - np.clip(ref[:n], -1, 1) * 32767.0).max() <= 1.5
