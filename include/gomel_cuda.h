@@ -180,9 +180,10 @@ int  gomel_from_phase_dev(gomel_ctx *ctx, const gomel_config *cfg, const float *
  * iteration and per rank boundary exactly two partial sums of Resolut-Window = 2816 floats cross:
  * the earlier rank's TAIL partial (-> next rank) and the later rank's HEAD partial (-> previous
  * rank); each side adds local + received (a+b == b+a, so both hold identical samples).
- * The library does not call NCCL itself: it exposes the four device pointers and a communication
- * stream, and orders that stream against its kernels with events; the caller issues the
- * send/recv pair (torch.distributed NCCL in gomel_b200/timesplit.py) on that stream.
+ * Two ways to move them: the library's own NCCL calls (gomel_ts_nccl_init / gomel_ts_run_nccl below, libnccl
+ * dlopen()ed), or the caller's collective library -- the session exposes the four device pointers and a
+ * communication stream and orders that stream against its kernels with events (gomel_ts_comm_begin / _end;
+ * torch.distributed NCCL in gomel_b200/timesplit.py).
  *   part: 0 = all tiles in one launch; 1 = only the tiles that touch a rank boundary (own stream);
  *         2 = the interior tiles -- lets the exchange of iteration i overlap its interior work. */
 typedef struct gomel_ts gomel_ts;
