@@ -263,6 +263,38 @@ def save_wav(file_path, audio_buffer, sample_rate):
     codec.save_wav_sf(file_path, audio_buffer, sample_rate)
 
 
+# ---- exported helpers of the Go package `phase` (phase/phase.go:155-188), Go codec flavour
+def LoadFlac(inputFile):
+    """phase.LoadFlac: samples / 32768, subframes appended block by block (phase/impl.go:351-381)"""
+    return codec.load_flac_go(inputFile, 256 * 128)[0]
+
+
+def LoadWav(inputFile):
+    """phase.LoadWav: left channel through beep's decoder (phase/impl.go:309-349)"""
+    return codec.load_wav(inputFile)[0]
+
+
+def LoadFlacSampleRate(inputFile):
+    """phase.LoadFlacSampleRate: (samples, sample rate) or ErrFileNotLoaded"""
+    mono, sr = codec.load_flac_go(inputFile, 256 * 128)
+    if len(mono) == 0 or sr == 0:
+        raise ErrFileNotLoaded()
+    return mono, int(sr)
+
+
+def LoadWavSampleRate(inputFile):
+    """phase.LoadWavSampleRate: (samples, sample rate) or ErrFileNotLoaded"""
+    mono, sr = codec.load_wav(inputFile)
+    if len(mono) == 0 or sr == 0:
+        raise ErrFileNotLoaded()
+    return mono, int(sr)
+
+
+def SaveWav(outputFile, vec, sr):
+    """phase.SaveWav -> dumpwav (phase/impl.go:280-307): truncating 16-bit PCM"""
+    return codec.save_wav(outputFile, vec, sr)
+
+
 pack_float16_to_bytes = codec.pack_f16_py
 unpack_bytes_to_float64 = codec.unpack_f16
 save_image = codec.phase_save_image_py
