@@ -663,7 +663,7 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic", "config": workload_config(n_gpus),
-            "precision": {"policy": "lead = max(4, iters - 28) Griffin-Lim iterations in float64 (k_gl_iter_f64), the rest in float32 (k_gl_iter)",
+            "precision": {"policy": "lead = max(16, iters - 16) Griffin-Lim iterations in float64 (k_gl_iter_f64), the rest in float32 (k_gl_iter)",
                           "float64_iterations": lead_it, "float32_iterations": (GL_ITERS - lead_it) if lead_it is not None else None,
                           "other_modes_device_resident": modes},
             "e2e": e2e,

@@ -225,7 +225,7 @@ func (x *Ctx) FromPhase(cfg Config, spec [][2]float64) ([]float64, error) {
 }
 
 // SetGLPrecision: at least `lead` float64 Griffin-Lim iterations first, at most `tail` float32 ones at the end
-// (tail < 0: unlimited).  Library defaults 4 and 28; (0, -1) is the all-float32 loop.
+// (tail < 0: unlimited).  Library defaults 16 and 16; (0, -1) is the all-float32 loop.
 func (x *Ctx) SetGLPrecision(lead, tail int) {
 	C.gomel_set_lead_f64(x.h, C.int(lead))
 	C.gomel_set_f32_tail(x.h, C.int(tail))

@@ -255,14 +255,14 @@ class Context:
         self.check(self.lib.gomel_set_tile_frames(self.h, int(t)))
 
     def set_lead_f64(self, k):
-        """minimum number of float64 lead iterations of Griffin-Lim (default 4); returns the previous value"""
+        """minimum number of float64 lead iterations of Griffin-Lim (default 16); returns the previous value"""
         rc = self.lib.gomel_set_lead_f64(self.h, int(k))
         if rc < 0:
             self.check(rc)
         return rc
 
     def set_f32_tail(self, n):
-        """maximum number of trailing float32 iterations (default 28; < 0 unlimited); returns the previous value"""
+        """maximum number of trailing float32 iterations (default 16; < 0 unlimited); returns the previous value"""
         rc = self.lib.gomel_set_f32_tail(self.h, int(n))
         if rc < 0:
             self.check(rc)

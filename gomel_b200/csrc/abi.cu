@@ -57,9 +57,9 @@ constexpr int kPipeSets = 3;
 enum PipeKind { P_IN = 0, P_OUT, P_INIT, P_PCM, P_MAGS32, P_MAGS64 };
 constexpr int pipe_slot(int set, int kind) { return S_PIPE + set * 8 + kind; }
 // Griffin-Lim precision policy (profiles/r02_gl_parity_sweep.md): at least kDefaultLeadF64 float64 iterations
-// first, and at most kDefaultF32Tail float32 iterations at the end -> lead = max(4, iters - 28)
-constexpr int kDefaultLeadF64 = 4;
-constexpr int kDefaultF32Tail = 28;
+// first, and at most kDefaultF32Tail float32 iterations at the end -> lead = max(16, iters - 16)
+constexpr int kDefaultLeadF64 = 16;
+constexpr int kDefaultF32Tail = 16;
 
 }  // namespace
 

@@ -50,7 +50,7 @@ struct Mel {                                         // mel/mel.go:10-27
     // extension: start-signal injection for parity runs (empty = draw U[0,1) like math/rand)
     std::vector<double> InitSignal;
     // extension: GOMEL_FLAG_F64 -- every Griffin-Lim iteration in float64 (default: the library's precision policy,
-    // max(4, iterations - 28) float64 lead iterations, then float32)
+    // max(16, iterations - 16) float64 lead iterations, then float32)
     bool Float64 = false;
 
     gomel_config config() const

@@ -54,14 +54,17 @@ typedef struct {
                             registered tables for this (n_fft, n_mels). */
 } gomel_config;
 
-/* Precision of the Griffin-Lim loop (mel.ISTFT, mel/mel.go:76-139).  The loop is ill-conditioned: a rounding
- * error made in iteration 0-1 ends ~300x larger after 32 iterations, one made in iteration 3 ~15x, and on flat
- * spectra (white noise, silence) float32 errors keep growing in bursts over long runs, so an all-float32 loop lands
- * between 7e-6 and 6e-4 of the float64 reference at 32 iterations and up to 5e-3 at 100
- * (profiles/r02_gl_parity_sweep.md).  Default policy: the first `lead` iterations run in float64 end to end on
- * the fused kernel of gl_f64.cuh, the rest in float32, with lead = max(4, GriffinLimIterations - 28) -- at least
- * four float64 iterations, at most 28 float32 ones: <= 2e-5 of the reference on every (clip, start signal) of the
- * sweep at 32 and at 100 iterations (tolerance 1e-4).  See gomel_set_lead_f64 / gomel_set_f32_tail.
+/* Precision of the Griffin-Lim loop (mel.ISTFT, mel/mel.go:76-139).  The loop is ill-conditioned while it has not
+ * settled: a float32 rounding error made in iteration 0-1 ends ~300x larger after 32 iterations, and for about one
+ * start signal in a hundred a trajectory passes near a singular point (a bin with a large target magnitude whose
+ * analysis value is almost zero) somewhere in the first ~16 iterations, where one float32 rounding flips the
+ * outcome by 1e-4 .. 1e-3.  Measured on 1,056 (clip, start signal) pairs at 32 iterations
+ * (profiles/r02_gl_parity_sweep.md): an all-float32 loop misses the 1e-4 tolerance on 3 % of the pairs, 4 float64
+ * lead iterations on 0.9 %, 12 on 0.1 %, 16 on none (worst 1.3e-5); on flat spectra float32 errors also grow in
+ * late bursts, so long float32 tails are unsafe at 100 iterations.  Default policy: the first `lead` iterations run
+ * in float64 end to end on the fused kernel of gl_f64.cuh, the rest in float32, with
+ * lead = max(16, GriffinLimIterations - 16) -- at least sixteen float64 iterations first, at most sixteen float32
+ * ones last (runs of <= 16 iterations are float64 throughout).  See gomel_set_lead_f64 / gomel_set_f32_tail.
  *   GOMEL_FLAG_F64      every iteration in float64 on the fused kernel (all from_mel entry points; the host-buffer
  *                       call then also reads the start signal and returns the waveform without a float32 step).
  *   GOMEL_FLAG_F64_REF  gomel_from_mel only: the round-1 strict path (one frame pair per CTA, spectra through HBM,
@@ -80,7 +83,7 @@ unsigned long long gomel_launch_count(gomel_ctx *ctx);
 /* frames per tile for the tiled kernels; 0 = automatic (default) */
 int  gomel_set_tile_frames(gomel_ctx *ctx, int tile_frames);
 /* Griffin-Lim precision policy: lead = max(lead_iters, GriffinLimIterations - f32_tail) float64 iterations, then
- * float32.  Defaults 4 and 28 (env GOMEL_LEAD_F64, GOMEL_F32_TAIL); lead_iters = 0 with f32_tail < 0 (unlimited)
+ * float32.  Defaults 16 and 16 (env GOMEL_LEAD_F64, GOMEL_F32_TAIL); lead_iters = 0 with f32_tail < 0 (unlimited)
  * is the all-float32 loop of round 1.  Each returns the previous value (unlimited tail: INT_MAX). */
 int  gomel_set_lead_f64(gomel_ctx *ctx, int lead_iters);
 int  gomel_set_f32_tail(gomel_ctx *ctx, int f32_tail);

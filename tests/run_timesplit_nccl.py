@@ -26,7 +26,7 @@ def main():
     from gomel_b200 import _lib, timesplit
     from oracle import oracle as O
     from util import rel_l2, synth_clip
-    iters, tile = 6, 8
+    iters, tile = 18, 8          # crosses the float64 -> float32 hand-over of the precision policy (16 lead iterations)
     ctx = _lib.Context(local)
     cfg = _lib.make_config(gl_iters=iters)
     ctx.set_mel_tables(cfg, 0.0, 16000.0)

@@ -120,7 +120,7 @@ def speed(clips=256):
                      "f32_frame_iter_per_s": fi * hn / (hms / 1e3) if hn else None,
                      "audio_s_per_s": clips * frames * 1280 / 44100 / (ms / 1e3)}
         print(name, json.dumps(res[name]), flush=True)
-    ctx.set_gl_precision(4, 28)
+    ctx.set_gl_precision(16, 16)
     json.dump(res, open(os.path.join(OUT, f"gl_modes_speed_{clips}.json"), "w"), indent=1)
 
 

@@ -29,14 +29,14 @@ ref64 = m.FromMel(mel.copy())
 m.Strict = False
 assert np.abs(out64 - ref64).max() < 1e-9
 # float64 lead iterations followed by float32 ones, several tilings; batched pipeline with a ragged last chunk
-m.GriffinLimIterations = 7
+m.GriffinLimIterations = 19
 import ctypes as C
 for tile in (0, 4, 10):
     ctx.set_tile_frames(tile)
     hy = m.FromMel(mel.copy())
     assert np.isfinite(hy).all()
 ctx.set_tile_frames(0)
-cfgb = _lib.make_config(gl_iters=6)
+cfgb = _lib.make_config(gl_iters=18)
 ctx.set_mel_tables(cfgb, 0.0, 16000.0)
 mb = np.stack([mel.astype(np.float32)] * 5)
 ob = np.empty((5, 4096 + (frames - 1) * 1280), np.float32)
@@ -56,8 +56,8 @@ fr2 = len(mel2) // 192
 init2 = np.random.default_rng(1).random(4096 + (fr2 - 1) * 1280).astype(np.float32)
 ts = timesplit.run_local(ctx, cfg, mel2, init2, 2, 2, tile_frames=4, overlap=True)
 assert np.isfinite(ts).all()
-cfg6 = _lib.make_config(gl_iters=6)
-ts6 = timesplit.run_local(ctx, cfg6, mel2, init2, 6, 2, tile_frames=4, overlap=True)        # crosses the float64 -> float32 hand-over
+cfg6 = _lib.make_config(gl_iters=18)
+ts6 = timesplit.run_local(ctx, cfg6, mel2, init2, 18, 2, tile_frames=4, overlap=True)        # crosses the float64 -> float32 hand-over
 assert np.isfinite(ts6).all()
 pcfg = _lib.make_config(n_mels=0, n_freqs=768, gl_iters=0)
 tp = timesplit.phase_istft_local(ctx, pcfg, ph.to_phase(wav2), 2, tile_frames=4)
