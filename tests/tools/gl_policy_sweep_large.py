@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Default precision policy against the all-float64 kernel on a larger population than the test-suite sweep:
-8 synthetic clips + white noise + silence + impulses, 10 s each, 32 start signals each at GL-32 (352 pairs) and 12 at
-GL-100 (132 pairs).  Writes gpurun_out/gl_policy_sweep_large.json."""
+"""Default precision policy against the all-float64 kernel on large populations (GPU box):
+    python tests/tools/gl_policy_sweep_large.py <iters> <n_seeds> <seed0> [seconds]
+11 clips (8 synthetic, white noise, silence, impulses) x n_seeds start signals; writes
+gpurun_out/gl_policy_sweep_<iters>_<seed0>_<seconds>.json."""
 import json
 import os
 import sys
@@ -13,28 +14,32 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 from gl_modes_check import O, rel_l2, run, synth_clip      # noqa: E402
 
-kinds = [("clip%d" % c, synth_clip(c, 10.0)) for c in range(8)]
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+n_seeds = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+seed0 = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+seconds = float(sys.argv[4]) if len(sys.argv) > 4 else 10.0
+n = int(round(seconds * 44100))
+kinds = [("clip%d" % c, synth_clip(c, seconds)) for c in range(8)]
 rng = np.random.default_rng(8)
-kinds.append(("white_noise", np.random.default_rng(77).uniform(-1, 1, 441000)))
-kinds.append(("silence", np.zeros(441000)))
-imp = np.zeros(441000)
-imp[rng.integers(0, 441000, 40)] = rng.uniform(-1, 1, 40)
+kinds.append(("white_noise", np.random.default_rng(77).uniform(-1, 1, n)))
+kinds.append(("silence", np.zeros(n)))
+imp = np.zeros(n)
+imp[rng.integers(0, n, max(4, n // 11000))] = rng.uniform(-1, 1, max(4, n // 11000))
 kinds.append(("impulses", imp))
 rows = []
-for iters, n_seeds in ((32, 32), (100, 12)):
-    for name, wav in kinds:
-        mel = O.to_mel(O.config(), wav)
-        errs = []
-        for s in range(n_seeds):
-            init = np.random.default_rng(1000 + s).random(440576)
-            e = rel_l2(run(mel, init, iters, False), run(mel, init, iters, True))
-            errs.append(e)
-            rows.append({"clip": name, "iters": iters, "seed": 1000 + s, "rel_l2": e})
-        print(f"GL-{iters} {name}: max {max(errs):.2e} median {np.median(errs):.2e}", flush=True)
-summ = {}
-for iters in (32, 100):
-    v = np.array([r["rel_l2"] for r in rows if r["iters"] == iters])
-    summ[iters] = {"pairs": int(len(v)), "max": float(v.max()), "median": float(np.median(v)), "p99": float(np.quantile(v, 0.99)),
-                   "pass_frac_1e-4": float(np.mean(v <= 1e-4))}
-print(json.dumps(summ, indent=1))
-json.dump({"rows": rows, "summary": summ}, open(os.path.join(ROOT, "gpurun_out", "gl_policy_sweep_large.json"), "w"), indent=1)
+for name, wav in kinds:
+    mel = O.to_mel(O.config(), wav)
+    frames = len(mel) // 192
+    ola = 4096 + (frames - 1) * 1280
+    errs = []
+    for s in range(n_seeds):
+        init = np.random.default_rng(seed0 + s).random(ola)
+        e = rel_l2(run(mel, init, iters, False), run(mel, init, iters, True))
+        errs.append(e)
+        rows.append({"clip": name, "iters": iters, "seed": seed0 + s, "rel_l2": e})
+    print(f"GL-{iters} {seconds:g}s {name}: max {max(errs):.2e} median {np.median(errs):.2e}", flush=True)
+v = np.array([r["rel_l2"] for r in rows])
+summ = {"iters": iters, "seconds": seconds, "pairs": int(len(v)), "max": float(v.max()), "median": float(np.median(v)),
+        "p99": float(np.quantile(v, 0.99)), "pass_frac_1e-4": float(np.mean(v <= 1e-4)), "misses": int(np.sum(v > 1e-4))}
+print(json.dumps(summ))
+json.dump({"rows": rows, "summary": summ}, open(os.path.join(ROOT, "gpurun_out", f"gl_policy_sweep_{iters}_{seed0}_{seconds:g}.json"), "w"), indent=1)
