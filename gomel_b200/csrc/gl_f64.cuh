@@ -230,16 +230,15 @@ __device__ __forceinline__ c64 shfl2(c64 a, int src)
 {
     return mk(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
-// 1/sqrt(n) to float64 rounding, branch free: float32 MUFU seed (relative error < 2^-22), two Newton steps
-// (error 1.5 e^2 each -> 1e-27 before rounding).  n = |X|^2 of a spectrum of O(1) signals: far inside the float32
-// range; n = 0 gives inf * 0 = NaN, which the caller's n > 0 select discards.
+// 1/sqrt(n) to float64 rounding, branch free: float32 MUFU seed y0 (relative error e0 < 2^-22), then ONE third-order
+// (Halley) step  y = y0 (1 + e/2 + 3 e^2/8),  e = 1 - n y0^2  -- remaining error O(e0^3) ~ 1e-20, five float64
+// instructions.  n = |X|^2 of a spectrum of O(1) signals: far inside the float32 range; n = 0 gives inf * 0 = NaN,
+// which the caller's n > 0 select discards.
 __device__ __forceinline__ double rsqrt_nr(double n)
 {
-    double y = (double)rsqrtf((float)n);
-    const double h = 0.5 * n;
-    y = fma(y, fma(-h * y, y, 0.5), y);
-    y = fma(y, fma(-h * y, y, 0.5), y);
-    return y;
+    const double y0 = (double)rsqrtf((float)n);
+    const double e = fma(-(n * y0), y0, 1.0);
+    return fma(y0, e * fma(0.375, e, 0.5), y0);
 }
 // cmplx.Rect(M, cmplx.Phase(X)) (mel/mel.go:98-102): M * X/|X|, Phase(0) = 0 -> (M, 0)
 __device__ __forceinline__ c64 subst(c64 X, double M)
