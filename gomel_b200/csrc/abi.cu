@@ -79,6 +79,7 @@ struct gomel_ctx {
     int lead_f64 = kDefaultLeadF64;   // gomel_set_lead_f64 / GOMEL_LEAD_F64
     int f32_tail = kDefaultF32Tail;   // gomel_set_f32_tail / GOMEL_F32_TAIL; < 0: unlimited
     double* d_tables_d64 = nullptr;   // gl_f64.cuh tables (built on first use)
+    double* d_tables_d64_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     float4* d_tables = nullptr;
     float4* d_tables_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     double* d_tables64 = nullptr;     // strict float64 path (built on first use)
@@ -346,15 +347,20 @@ int ensure_tables_d64(gomel_ctx* ctx)
     for (int n = 0; n < kN / 2; n++) win[n] = 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1)));
     CU(cudaMalloc(&ctx->d_tables_d64, D::kTableBytes));
     CU(cudaMemcpy(ctx->d_tables_d64, blob.data(), D::kTableBytes, cudaMemcpyHostToDevice));
+    const int n_alt = 256 * kAltFS;
+    for (int n = 0; n < kN / 2; n++) win[n] = n < n_alt / 2 ? 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(n_alt - 1))) : 0.0;
+    CU(cudaMalloc(&ctx->d_tables_d64_alt, D::kTableBytes));
+    CU(cudaMemcpy(ctx->d_tables_d64_alt, blob.data(), D::kTableBytes, cudaMemcpyHostToDevice));
     CU(cudaFuncSetAttribute(D::k_gl_iter_f64<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes));
+    CU(cudaFuncSetAttribute(D::k_gl_iter_f64<kAltHS, kAltFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes));
     return 0;
 }
 
 // How many of `iters` Griffin-Lim iterations run in float64 (gl_f64.cuh) before the float32 kernel takes over.
-// GOMEL_FLAG_F64: all of them.  The Resolut 2048 geometry has no float64 kernel.
+// GOMEL_FLAG_F64: all of them.
 int lead_iters(const gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo)
 {
-    if (geo.alt) return 0;
+    (void)geo;
     const int iters = cfg->gl_iters < 0 ? 0 : cfg->gl_iters;
     if (cfg->flags & GOMEL_FLAG_F64) return iters;
     int lead = ctx->lead_f64;
@@ -481,7 +487,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
         CU(cudaEventRecord(ctx->ev_l0, ctx->st));
         if (int rc = fork()) return rc;
         d64::GLParams p = {};
-        p.tables = ctx->d_tables_d64; p.tl = tl; p.mags = io.mags64;
+        p.tables = geo.alt ? ctx->d_tables_d64_alt : ctx->d_tables_d64; p.tl = tl; p.mags = io.mags64;
         p.hb_tiles = hb_tiles; p.tile_lo = 0; p.tiles_in_launch = tl.n_tiles;
         for (int i = 0; i < lead; i++) {
             p.sig_in = cur; p.sig_out = sg[w];
@@ -490,7 +496,8 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
             for (int g = 0; g < ns; g++) {
                 p.clip0 = c_lo(g);
                 const unsigned gg = (unsigned)((long)(c_lo(g + 1) - c_lo(g)) * tl.n_tiles);
-                d64::k_gl_iter_f64<kHS><<<gg, kThreads, d64::kSmemBytes, gs[g]>>>(p);
+                if (geo.alt) d64::k_gl_iter_f64<kAltHS, kAltFS><<<gg, kThreads, d64::kSmemBytes, gs[g]>>>(p);
+                else d64::k_gl_iter_f64<kHS><<<gg, kThreads, d64::kSmemBytes, gs[g]>>>(p);
                 ctx->launches++;
             }
             cur = sg[w]; w ^= 1;
@@ -819,7 +826,7 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_tables_alt);
     cudaFree(ctx->d_tables64);
-    cudaFree(ctx->d_tables_d64);
+    cudaFree(ctx->d_tables_d64); cudaFree(ctx->d_tables_d64_alt);
     cudaEventDestroy(ctx->ev_l0); cudaEventDestroy(ctx->ev_l1);
     for (MelTables& t : ctx->mel_tabs) t.release();
     cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
@@ -982,7 +989,6 @@ int gomel_from_mel(gomel_ctx* ctx, const gomel_config* cfg, const double* mel, l
     if (int rc = check_cfg(ctx, cfg, ref64 ? nullptr : &geo)) return rc;
     if (!mel || !wav_out || n_frames <= 0 || cfg->n_mels <= 0) return fail(ctx, GOMEL_E_ARG, "bad argument");
     if (cfg->gl_iters < 0) return fail(ctx, GOMEL_E_ARG, "GriffinLimIterations < 0");
-    if (geo.alt && (cfg->flags & GOMEL_FLAG_F64)) return fail(ctx, GOMEL_E_UNSUPPORTED, "GOMEL_FLAG_F64 needs Resolut=4096, Window=1280");
     const long ola = geo.ola(n_frames);
     const long n_mel = n_frames * 2L * cfg->n_mels;
     void *dmel, *dinit64 = nullptr, *dinit = nullptr, *dout, *dout64;

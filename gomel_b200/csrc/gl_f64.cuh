@@ -51,9 +51,11 @@ __device__ __forceinline__ Smem carve(unsigned char* base)
     return s;
 }
 
+// Hann coefficient of sample n = t + 256*m of an FS*256-sample frame (symmetric window, first half stored)
+template <int FS>
 __device__ __forceinline__ double win_at(const double* win, int m, int t)
 {
-    return (m < 8) ? win[m * 256 + t] : win[(15 - m) * 256 + (255 - t)];
+    return (m < FS / 2) ? win[m * 256 + t] : win[(FS - 1 - m) * 256 + (255 - t)];
 }
 
 // the thread <-> digit mapping of fft4096.cuh with this file's row padding
@@ -271,7 +273,9 @@ struct GLParams {
 // One Griffin-Lim iteration (one pass of the loop body of mel.ISTFT, mel/mel.go:85-136) in float64.
 // Tile edges exactly as in k_gl_iter: the earlier tile's partial sum of a shared region goes to sig_out
 // (its tail), the later tile's to hb_out (its head); every reader adds the two.
-template <int HS>
+// FS = frame slots (Resolut / 256): 16 is the native frame; 8 (Resolut 2048, the mel.NewMel default) runs the frame
+// zero-extended through the same 4096-point core, its spectrum on the even core bins (cf. k_gl_iter).
+template <int HS, int FS = 16>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
         const double2* g = reinterpret_cast<const double2*>(p.tables);
         for (int i = L.t; i < kTableBytes / 16; i += kThreads) d[i] = __ldg(g + i);
     }
-    constexpr int NR = 16 + HS, KEEP = 16 - HS, H = 256 * HS, HALO = KEEP * 256;
+    constexpr int NR = FS + HS, KEEP = FS - HS, H = 256 * HS, HALO = KEEP * 256;
     int tile, clip;
     if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
     else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = p.clip0 + blockIdx.x / p.tiles_in_launch; }
@@ -336,7 +340,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
                 for (int j = 0; j < NR; j++) raw[j] = ld(off0 + j * 256);
             }
 #pragma unroll
-            for (int m = 0; m < 16; m++) { const double w = win_at(s.win, m, t); v[m] = mk(raw[m] * w, raw[m + HS] * w); }
+            for (int m = 0; m < 16; m++) {
+                if (m < FS) { const double w = win_at<FS>(s.win, m, t); v[m] = mk(raw[m] * w, raw[m + HS] * w); }
+                else v[m] = mk(0.0, 0.0);
+            }
         }
         // pull the next pair's new signal rows and both pairs' magnitude lines towards L2 while this pair computes
         if (pr + 1 < npairs) {
@@ -412,14 +419,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
 #pragma unroll
             for (int r = 0; r < NR; r++) o[r] = 0.0;
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const double w = win_at(s.win, m, t);
+            for (int m = 0; m < FS; m++) {
+                const double w = win_at<FS>(s.win, m, t);
                 o[m] = v[m].x * w;                        // A first, then B: ascending frame order
             }
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const double w = win_at(s.win, m, t);
-                o[m + HS] = (m + HS < 16) ? fma(v[m].y, w, o[m + HS]) : v[m].y * w;
+            for (int m = 0; m < FS; m++) {
+                const double w = win_at<FS>(s.win, m, t);
+                o[m + HS] = (m + HS < FS) ? fma(v[m].y, w, o[m + HS]) : v[m].y * w;
             }
             const bool fast = off0 + NR * 256 <= lim && (!has_prev || off0 >= HALO);
             if (fast && pr > 0) {

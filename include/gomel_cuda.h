@@ -14,9 +14,9 @@
  *     serialised by an internal mutex and may come from any OS thread (cgo hops threads).
  *   - this build supports Resolut (n_fft) = 4096 and Window (hop) = 1280 (the configuration of
  *     cmd/tomel, cmd/towav, cmd/tophase, cmd/fromphase and of NewPhase) on every entry point,
- *     and Resolut 2048 / Window 256 (the mel.NewMel defaults, mel/mel.go:37-38) on the float32
- *     mel entry points (gomel_to_mel*, gomel_from_mel* without GOMEL_FLAG_F64,
- *     gomel_set_mel_tables); anything else returns GOMEL_E_UNSUPPORTED.  There is NO CPU fallback.
+ *     and Resolut 2048 / Window 256 (the mel.NewMel defaults, mel/mel.go:37-38) on the mel entry
+ *     points (gomel_to_mel*, gomel_from_mel* except GOMEL_FLAG_F64_REF, gomel_set_mel_tables);
+ *     anything else returns GOMEL_E_UNSUPPORTED.  There is NO CPU fallback.
  */
 #ifndef GOMEL_CUDA_H
 #define GOMEL_CUDA_H

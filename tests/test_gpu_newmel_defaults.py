@@ -77,6 +77,27 @@ def test_from_mel_defaults_32_iterations(ctx, oracle, restore_tables):
     assert rel_l2(got, ref) < TOL_GL, rel_l2(got, ref)
 
 
+@pytest.mark.parametrize("seconds,iters,tile", [(0.3, 1, 0), (1.0, 3, 6), (1.0, 20, 8), (2.2, 32, 0)])
+def test_from_mel_defaults_float64_matches_oracle(ctx, oracle, restore_tables, seconds, iters, tile):
+    """the float64 kernel on the Resolut 2048 / Window 256 geometry (frame zero-extended through the 4096-point core):
+    GOMEL_FLAG_F64 reproduces the oracle to 1e-10 here too, and the default policy (<= 16 iterations: all float64) with it"""
+    wav = synth_clip(23, seconds)
+    ocfg = _ocfg(oracle, iters)
+    mel = oracle.to_mel(ocfg, wav)
+    frames = len(mel) // 160
+    init = np.random.default_rng(7002).random(2048 + (frames - 1) * 256)
+    ref = oracle.from_mel(ocfg, mel, init)
+    ctx.set_tile_frames(tile)
+    for strict in (True, False):
+        m = _newmel(iters)
+        m.Strict = strict
+        m.InitSignal = init
+        got = m.FromMel(mel.copy())
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < (1e-10 if (strict or iters <= 16) else TOL_GL), (strict, rel_l2(got, ref))
+    ctx.set_tile_frames(0)
+
+
 @pytest.mark.parametrize("frames", [1, 2, 3, 7, 8, 9, 15, 16, 17])
 def test_from_mel_defaults_tiny_frame_counts(ctx, oracle, restore_tables, frames):
     rng = np.random.default_rng(frames)
@@ -154,7 +175,7 @@ def test_geometries_outside_the_two_supported_fail_loudly(ctx, lib, restore_tabl
         p.ToPhase(np.zeros(10000))
     assert e.value.code == lib.E_UNSUPPORTED
     s = NewMel()
-    s.Strict = True                                     # the float64 instrument is native-geometry only
+    s.Strict = "ref"                                    # the round-1 strict test instrument is native-geometry only
     with pytest.raises(lib.GomelError) as e:
         s.FromMel(np.zeros((160 * 4, 2)))
     assert e.value.code == lib.E_UNSUPPORTED
