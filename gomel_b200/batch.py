@@ -1,6 +1,6 @@
 """Directory-level batch tools on top of the batched C ABI: many files per GPU call.
 
-    tomel_dir(in_dir, out_dir, mel)     every *.wav  ->  <name>.png, identical to Mel.ToMelWav per file
+    tomel_dir(in_dir, out_dir, mel)     every *.wav / *.flac  ->  <name>.png, identical to Mel.ToMelWav / ToMelFlac per file
     towav_dir(in_dir, out_dir, mel)     every *.png  ->  <name>.wav, identical to Mel.ToWavPng per file (same start signal)
 
 ToMel frames depend only on local samples, so clips of different length share one batch: every clip is
@@ -18,14 +18,15 @@ from . import _lib, codec
 
 def tomel_dir(in_dir, out_dir, mel, chunk=64):
     """mel: a configured gomel_b200.Mel.  Returns the list of PNG paths written."""
-    files = sorted(glob.glob(os.path.join(in_dir, "*.wav")))
+    files = sorted(glob.glob(os.path.join(in_dir, "*.wav")) + glob.glob(os.path.join(in_dir, "*.flac")))
     os.makedirs(out_dir, exist_ok=True)
     cfg = mel._cfg()
     ctx = mel._ctx(cfg)
     written = []
     for c0 in range(0, len(files), chunk):
         part = files[c0:c0 + chunk]
-        clips = [codec.load_wav(f) for f in part]
+        # per file exactly what the single-file methods decode: loadwav, or loadflac with the mel package's 1/65536
+        clips = [codec.load_flac_go(f, 256 * 256) if f.endswith(".flac") else codec.load_wav(f) for f in part]
         clips = [(f, b, sr) for f, (b, sr) in zip(part, clips) if len(b) > 0]
         if not clips:
             continue

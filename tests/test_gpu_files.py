@@ -186,9 +186,13 @@ def test_batch_directory_tools_match_single_file_api(tmp_path, oracle, ctx):
     lens = {"a": 0.7, "b": 1.3, "c": 0.7, "d": 0.2}
     for k, (name, secs) in enumerate(lens.items()):
         codec.save_wav(str(ind / f"{name}.wav"), synth_clip(80 + k, secs), 44100)
+    _flac_fixture(str(ind / "e.flac"), 0.5, 44100, True, 9)                  # a stereo FLAC file in the same directory
     m = _mel()
     out = batch.tomel_dir(str(ind), str(pngd), m, chunk=3)
-    assert len(out) == 4
+    assert len(out) == 5
+    m.ToMelFlac(str(ind / "e.flac"), str(pngd1 / "e.flac.png"))
+    assert np.array_equal(codec.read_png(str(pngd / "e.flac.png")), codec.read_png(str(pngd1 / "e.flac.png")))
+    os.remove(str(pngd / "e.flac.png"))
     for name in lens:
         m.ToMelWav(str(ind / f"{name}.wav"), str(pngd1 / f"{name}.wav.png"))
         a, b = codec.read_png(str(pngd / f"{name}.wav.png")), codec.read_png(str(pngd1 / f"{name}.wav.png"))
