@@ -339,10 +339,10 @@ int ensure_tables_d64(gomel_ctx* ctx)
             T1[(i * 256 + t) * 2] = std::cos(a); T1[(i * 256 + t) * 2 + 1] = -std::sin(a);
         }
     }
-    for (int k = 0; k < 16; k++)                     // stage 2: full table W256^(n0*k)
+    for (int i = 0; i < 4; i++)                      // stage 2: powers 1,2,4,8 of W256^n0
         for (int n0 = 0; n0 < 16; n0++) {
-            const double a = two_pi * (double)((n0 * k) % 256) / 256.0;
-            T2[(k * 16 + n0) * 2] = std::cos(a); T2[(k * 16 + n0) * 2 + 1] = -std::sin(a);
+            const double a = two_pi * (double)((n0 * pw[i]) % 256) / 256.0;
+            T2[(i * 16 + n0) * 2] = std::cos(a); T2[(i * 16 + n0) * 2 + 1] = -std::sin(a);
         }
     for (int n = 0; n < kN / 2; n++) win[n] = 0.5 * (1.0 - std::cos(two_pi * (double)n / (double)(kN - 1)));
     CU(cudaMalloc(&ctx->d_tables_d64, D::kTableBytes));

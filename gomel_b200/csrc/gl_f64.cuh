@@ -30,11 +30,11 @@ constexpr int kPlane = 16 * kRow;                          // 272
 constexpr int kXchgCells = 16 * kPlane;                    // 4352
 constexpr int kXchgBytes = kXchgCells * 16;                // 69,632 B
 constexpr int kT1Cells = 4 * 256;                          // stage 1: powers 1,2,4,8 of each lane's root W4096^t
-constexpr int kT2Cells = 16 * 16;                          // stage 2: all powers of W256^n0 (4 KB: cheaper than 11 products)
+constexpr int kT2Cells = 4 * 16;                           // stage 2: powers 1,2,4,8 of W256^n0
 constexpr int kWinCells = 2048;                            // first half of the symmetric Hann window, [m][t]
-constexpr int kTableBytes = (kT1Cells + kT2Cells) * 16 + kWinCells * 8;      // 33,792 B
+constexpr int kTableBytes = (kT1Cells + kT2Cells) * 16 + kWinCells * 8;      // 30,720 B
 constexpr int kScratchBytes = 32 * 16;                     // the special coset's hand-over (warp 0)
-constexpr int kSmemBytes = kTableBytes + kXchgBytes + kScratchBytes;         // 103,936 B -> 2 CTAs / SM
+constexpr int kSmemBytes = kTableBytes + kXchgBytes + kScratchBytes;         // 100,864 B -> 2 CTAs / SM
 
 using c64 = double2;
 
@@ -162,15 +162,10 @@ __device__ __forceinline__ void radix16(c64 (&v)[16])
     for (int i = 0; i < 16; i++) v[i] = o[i];
 }
 
-// external twiddles from a full table T[k][lane] = w^k
-template <bool INV>
-__device__ __forceinline__ void apply_twiddles_full(c64 (&v)[16], const c64* T, int rowlen, int lane)
-{
-#pragma unroll
-    for (int k = 1; k < 16; k++) v[k] = cmul_tw<INV>(v[k], T[k * rowlen + lane]);
-}
-
-// external twiddles v[k] *= w^k (forward) or conj(w)^k (inverse); the table holds w^1, w^2, w^4, w^8
+// external twiddles v[k] *= w^k (forward) or conj(w)^k (inverse); the table holds w^1, w^2, w^4, w^8 and the other
+// eleven powers are products.  Measured on both stages against full tables: the kernel's shared-memory pipe is as
+// busy as its FP64 pipe (54 % / 51 %) and a table load costs more than the 4-instruction product it saves (a full
+// stage-2 table: +88 shared-memory wavefronts, -88 FP64 instructions per pair, 5 % slower).
 template <bool INV>
 __device__ __forceinline__ void apply_twiddles(c64 (&v)[16], const c64* T, int rowlen, int lane)
 {
@@ -199,7 +194,7 @@ __device__ __forceinline__ void fft_fwd(c64 (&v)[16], const Smem& s, const Lanes
 #pragma unroll
     for (int r = 0; r < 16; r++) v[r] = s.xb[L.base_b + r * kRow];
     radix16<false>(v);
-    apply_twiddles_full<false>(v, s.T2, 16, L.n0b);
+    apply_twiddles<false>(v, s.T2, 16, L.n0b);
 #pragma unroll
     for (int r = 0; r < 16; r++) s.xb[L.base_b + r * kRow] = v[r];
     __syncwarp();                                   // plane k0 is private to this half-warp
@@ -212,7 +207,7 @@ __device__ __forceinline__ void fft_fwd(c64 (&v)[16], const Smem& s, const Lanes
 __device__ __forceinline__ void fft_inv(c64 (&v)[16], const Smem& s, const Lanes& L)
 {
     radix16<true>(v);
-    apply_twiddles_full<true>(v, s.T2, 16, L.k1c);
+    apply_twiddles<true>(v, s.T2, 16, L.k1c);
 #pragma unroll
     for (int c = 0; c < 16; c++) s.xb[L.base_c + c] = v[c];
     __syncwarp();
@@ -345,13 +340,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
                 else v[m] = mk(0.0, 0.0);
             }
         }
-        // pull the next pair's new signal rows and both pairs' magnitude lines towards L2 while this pair computes
+        // pull the next pair's new signal rows and both of its magnitude lines towards L2 while this pair computes:
+        // two contiguous spans, one 128-byte line per lane (3 instructions per thread instead of 26 -- the LSU pipe is
+        // this kernel's co-bottleneck)
         if (pr + 1 < npairs) {
-            const int r0 = off0 + 2 * H + KEEP * 256 + t;
-#pragma unroll
-            for (int j = 0; j < 2 * HS; j++) if (r0 + j * 256 < lim) prefetch_l2(sin_ + r0 + j * 256);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { prefetch_l2(mA + 2 * kMagStride + j * 256); prefetch_l2(mB + 2 * kMagStride + j * 256); }
+            const int r0 = off0 + 2 * H + KEEP * 256;
+            int ns = lim - r0; ns = ns < 2 * H ? ns : 2 * H;                       // doubles
+            const char* sp = reinterpret_cast<const char*>(sin_ + r0);
+            if (t * 16 < ns) prefetch_l2(sp + t * 128);
+            const bool twoM = (f0 + 2 * pr + 3) < p.tl.n_frames;
+            const int nm = (twoM ? 2 : 1) * kMagStride;                            // doubles
+            const char* mp = reinterpret_cast<const char*>(mrow + (long)(2 * pr + 2) * kMagStride);
+            if (t * 16 < nm) prefetch_l2(mp + t * 128);
+            if ((t + 256) * 16 < nm) prefetch_l2(mp + (t + 256) * 128);
         }
 
         fft_fwd(v, s, L);
