@@ -642,7 +642,7 @@ def run_product(args):
                                               "float32 units (18,436 B) the fraction is half of `frac`",
                     "frac_in_float32_units": l_ach / peak / 2, "avg_launch_ms": l_s * 1e3,
                     "launches_timed": lead_n, "kernel_share_of_step": lead_ms / dev_ms,
-                    "practical_bound": "FP64 pipe 51 % busy + shared-memory pipe 47 % busy at 16 warps per SM (profiles/r02_gl_iter_f64_v2.md)",
+                    "practical_bound": "FP64 pipe 57 % busy + LSU / shared-memory data pipe 53 % busy at 16 warps per SM (profiles/r02_gl_iter_f64_v3.md)",
                     "launch_note": f32_rec["launch_note"],
                     "frame_iterations_per_s_per_gpu": clips * frames * lead_n / (lead_ms / 1e3)}
                 # `roofline` describes the kernel with the larger share of the step; the other one rides along

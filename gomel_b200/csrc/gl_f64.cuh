@@ -32,9 +32,9 @@ constexpr int kXchgBytes = kXchgCells * 16;                // 69,632 B
 constexpr int kT1Cells = 4 * 256;                          // stage 1: powers 1,2,4,8 of each lane's root W4096^t
 constexpr int kT2Cells = 4 * 16;                           // stage 2: powers 1,2,4,8 of W256^n0
 constexpr int kWinCells = 2048;                            // first half of the symmetric Hann window, [m][t]
-constexpr int kTableBytes = (kT1Cells + kT2Cells) * 16 + kWinCells * 8;      // 30,720 B
+constexpr int kTableBytes = (kT1Cells + kT2Cells) * 16 + kWinCells * 8;      // 33,792 B
 constexpr int kScratchBytes = 32 * 16;                     // the special coset's hand-over (warp 0)
-constexpr int kSmemBytes = kTableBytes + kXchgBytes + kScratchBytes;         // 100,864 B -> 2 CTAs / SM
+constexpr int kSmemBytes = kTableBytes + kXchgBytes + kScratchBytes;         // 103,936 B -> 2 CTAs / SM
 
 using c64 = double2;
 
