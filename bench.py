@@ -719,6 +719,21 @@ def run_product(args):
                             "iteration_kernels_ms": lms + hms, "float64_iterations": ln, "float32_iterations": hn,
                             "note": "the rest of the call is the pageable float64 host copies (mel 1 MB + start signal 3.5 MB in, 3.5 MB out), "
                                     "magnitudes, conversions and one stream synchronisation"}
+        # the same single clip through the pinned float32 call (start signal drawn on the device): what a caller that
+        # keeps its own pinned buffers pays -- no pageable staging, 0.26 MB in, 1.75 MB out
+        pinned = {"workload": "gomel_from_mel_batch_host, one 10 s clip, pinned float32 host buffers, start signal from the seed"}
+        for name, it_ in (("gl2", 2), ("gl32", GL_ITERS)):
+            c1 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=it_)
+            one = lambda sd: ctx.check(ctx.lib.gomel_from_mel_batch_host(ctx.h, C.byref(c1), h_mel.ctypes.data_as(C.c_void_p), 1, frames,
+                                                                        None, sd, h_out.ctypes.data_as(C.c_void_p), 1))
+            for w in range(3):
+                one(w)
+            t0 = time.perf_counter()
+            for w in range(10):
+                one(10 + w)
+            sec = (time.perf_counter() - t0) / 10
+            pinned[name] = {"ms": sec * 1e3, "audio_s_per_s": frames * HOP / SR / sec}
+        single["pinned_float32_call"] = pinned
         line["single_clip_host_api"] = single
         line["gl100"] = {"workload": f"configs[3] with 100 iterations (84 float64 + 16 float32 under the policy), {clips} clips, device-resident",
                          "ms_per_step": ms100,
