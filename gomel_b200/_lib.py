@@ -44,6 +44,8 @@ SIGNATURES = {
     "gomel_set_tile_frames": (C.c_int, [_vp, C.c_int]),
     "gomel_set_lead_f64": (C.c_int, [_vp, C.c_int]),
     "gomel_set_f32_tail": (C.c_int, [_vp, C.c_int]),
+    "gomel_set_gl_guard": (C.c_int, [_vp, C.c_float, _fp]),
+    "gomel_last_gl_guard": (C.c_int, [_vp, _ip, _ip, _fp, _fp, C.c_int]),
     "gomel_frames": (C.c_int, [_cp, C.c_long, _lp, _lp, _lp]),
     "gomel_ola_len": (C.c_long, [_cp, C.c_long]),
     "gomel_set_mel_tables": (C.c_int, [_vp, _cp, _ip, _ip, _dp, _ip, _ip, _dp]),
@@ -267,6 +269,19 @@ class Context:
         if rc < 0:
             self.check(rc)
         return -1 if rc == 0x7fffffff else rc
+
+    def set_gl_guard(self, threshold):
+        """leverage threshold of the float32 tail's singular-bin guard (default 5e4, 0 disables); returns the previous value"""
+        prev = C.c_float()
+        self.check(self.lib.gomel_set_gl_guard(self.h, float(threshold), C.byref(prev)))
+        return prev.value
+
+    def last_gl_guard(self, cap=0):
+        """-> (clips the guard saw, clips re-run in float64, largest leverage, leverage of the first `cap` clips)"""
+        n, r, mx = C.c_int(), C.c_int(), C.c_float()
+        lev = np.zeros(max(cap, 1), np.float32)
+        self.check(self.lib.gomel_last_gl_guard(self.h, C.byref(n), C.byref(r), C.byref(mx), lev.ctypes.data_as(_fp), int(cap)))
+        return n.value, r.value, mx.value, lev[:min(cap, n.value)]
 
     def set_gl_precision(self, lead, tail):
         """-> (previous lead, previous tail)"""

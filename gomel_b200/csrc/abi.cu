@@ -51,7 +51,7 @@ constexpr size_t kMaxMelTables = 64;
 static_assert(sizeof(gomel_config) == 72, "gomel_config layout is part of the ABI (ctypes / cgo mirror it)");
 
 enum Scratch { S_F64IN = 0, S_SIG64A, S_SIG64B, S_Y64, S_MAGS64, S_F64IN2, S_F64OUT, S_F32A, S_F32B, S_SIGTMP, S_INIT, S_HB0, S_HB1, S_MAGS,
-               S_MISC, S_LSIGA, S_LSIGB, S_LHB0, S_LHB1, S_LMAGS, S_PIPE, S_COUNT = S_PIPE + 3 * 8 };
+               S_MISC, S_LSIGA, S_LSIGB, S_LHB0, S_LHB1, S_LMAGS, S_GUARD, S_GHB0, S_GHB1, S_PIPE, S_COUNT = S_PIPE + 3 * 8 };
 // chunk buffers of the pipelined host batches: kPipeSets sets of (mel | signal in, out, init, pcm, mags32, mags64)
 constexpr int kPipeSets = 3;
 enum PipeKind { P_IN = 0, P_OUT, P_INIT, P_PCM, P_MAGS32, P_MAGS64 };
@@ -60,6 +60,9 @@ constexpr int pipe_slot(int set, int kind) { return S_PIPE + set * 8 + kind; }
 // first, and at most kDefaultF32Tail float32 iterations at the end -> lead = max(16, iters - 16)
 constexpr int kDefaultLeadF64 = 16;
 constexpr int kDefaultF32Tail = 16;
+// Singular-bin guard of the float32 tail (profiles/r02_gl_guard.md): clips whose statistic exceeds this many clip-rms
+// units have their tail re-run in float64.  0 disables.
+constexpr float kDefaultGlGuard = 5.0e4f;
 
 }  // namespace
 
@@ -78,6 +81,9 @@ struct gomel_ctx {
     int lead_launches = 0;    // float64 lead iterations of the last Griffin-Lim, bracketed by ev_l0/ev_l1
     int lead_f64 = kDefaultLeadF64;   // gomel_set_lead_f64 / GOMEL_LEAD_F64
     int f32_tail = kDefaultF32Tail;   // gomel_set_f32_tail / GOMEL_F32_TAIL; < 0: unlimited
+    float gl_guard = kDefaultGlGuard; // gomel_set_gl_guard / GOMEL_GL_GUARD
+    int guard_clips = 0;              // clips of the last guarded Griffin-Lim run (statistics in scratch[S_GUARD]); 0: none
+    float guard_thr_units = 0;        // the threshold that run used, in statistic units
     double* d_tables_d64 = nullptr;   // gl_f64.cuh tables (built on first use)
     double* d_tables_d64_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     float4* d_tables = nullptr;
@@ -353,6 +359,8 @@ int ensure_tables_d64(gomel_ctx* ctx)
     CU(cudaMemcpy(ctx->d_tables_d64_alt, blob.data(), D::kTableBytes, cudaMemcpyHostToDevice));
     CU(cudaFuncSetAttribute(D::k_gl_iter_f64<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes));
     CU(cudaFuncSetAttribute(D::k_gl_iter_f64<kAltHS, kAltFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes));
+    CU((cudaFuncSetAttribute(D::k_gl_iter_f64<kHS, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes)));
+    CU((cudaFuncSetAttribute(D::k_gl_iter_f64<kAltHS, kAltFS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D::kSmemBytes)));
     return 0;
 }
 
@@ -375,6 +383,21 @@ struct GlIO {
     const float* init32 = nullptr; const double* init64 = nullptr;
     float* out32 = nullptr; double* out64 = nullptr;
 };
+
+// tiling of the guard's float64 re-run: few clips, so short tiles (8 frames) keep one iteration at a few pair times
+Tiling redo_tiling(const Tiling& tl, const Geo& geo)
+{
+    (void)geo;
+    Tiling rt = tl;
+    int T = 8;
+    const int fr_even = tl.n_frames + (tl.n_frames & 1);
+    if (T > fr_even) T = fr_even;
+    if (T < 4) T = 4;
+    rt.tile_frames = T;
+    rt.n_tiles = (tl.n_frames + T - 1) / T;
+    rt.edge_first = rt.edge_last = 0;
+    return rt;
+}
 
 // grow-only scratch of gl_dev for a batch of this size; called up front by the chunked pipelines so that no
 // (device-synchronising) reallocation happens between chunks
@@ -400,12 +423,23 @@ int gl_reserve(gomel_ctx* ctx, const gomel_config* cfg, int n_clips, long n_fram
         if (int rc = ensure(ctx, S_LHB0, hb_elems * 8, &b)) return rc;
         if (int rc = ensure(ctx, S_LHB1, hb_elems * 8, &b)) return rc;
         if (int rc = ensure_tables_d64(ctx)) return rc;
+        if (iters - lead > 0 && ctx->gl_guard > 0.0f) {
+            // the guard's statistic | clip scale | selection list | count, and the re-run's own head-partial buffers
+            // (its tiles are short: it is latency bound, and indexed by list slot)
+            if (int rc = ensure(ctx, S_GUARD, (size_t)n_clips * 12 + 16, &b)) return rc;
+            const Tiling rt = redo_tiling(tl, geo);
+            const size_t rhb = (size_t)n_clips * (rt.n_tiles + 1) * geo.halo * 8 + 32;
+            if (int rc = ensure(ctx, S_GHB0, rhb, &b)) return rc;
+            if (int rc = ensure(ctx, S_GHB1, rhb, &b)) return rc;
+        }
     }
     return 0;
 }
 
+// the float64 state at the hand-over, kept for the guard's re-run of selected clips
+struct RedoState { double* fin = nullptr; double* other = nullptr; double* hb[2] = { nullptr, nullptr }; const double* mags64 = nullptr; };
 int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl,
-               const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs);
+               const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs, const RedoState* redo);
 
 int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips, long n_frames,
            unsigned long long seed, long sig_stride)
@@ -437,7 +471,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
         ctx->launches++;
         init32 = b;
     }
-    ctx->hot_launches = 0; ctx->lead_launches = 0;
+    ctx->hot_launches = 0; ctx->lead_launches = 0; ctx->guard_clips = 0;
     if (iters == 0) {       // mel/mel.go:85: zero iterations return the start signal
         if (io.out64) {
             if (init64) CU(cudaMemcpyAsync(io.out64, init64, (size_t)n_sig * 8, cudaMemcpyDeviceToDevice, ctx->st));
@@ -473,6 +507,7 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
 
     float* tmp = (float*)ctx->scratch[S_SIGTMP];
     const float* cur32 = init32;
+    RedoState redo;
     // ---------------- float64 lead iterations
     if (lead > 0) {
         double* sg[2] = { (double*)ctx->scratch[S_LSIGA], (double*)ctx->scratch[S_LSIGB] };
@@ -527,13 +562,15 @@ int gl_dev(gomel_ctx* ctx, const gomel_config* cfg, const GlIO& io, int n_clips,
         ctx->lead_launches = lead;
         cur32 = conv;
         if (iters == lead) { CU(cudaGetLastError()); return 0; }
+        redo.fin = fin; redo.other = (fin == sg[0]) ? sg[1] : sg[0]; redo.hb[0] = hb[0]; redo.hb[1] = hb[1]; redo.mags64 = io.mags64;
     }
     // ---------------- float32 iterations
-    return gl_dev_f32(ctx, cfg, geo, io, tl, cur32, tmp, n_clips, iters, lead, ns, gs);
+    return gl_dev_f32(ctx, cfg, geo, io, tl, cur32, tmp, n_clips, iters, lead, ns, gs,
+                      (redo.fin && ctx->gl_guard > 0.0f && io.out32) ? &redo : nullptr);
 }
 
 int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const GlIO& io, const Tiling& tl,
-               const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs)
+               const float* cur32, float* tmp, int n_clips, int iters, int lead, int ns, cudaStream_t* gs, const RedoState* redo)
 {
     (void)cfg;
     const int hb_tiles = tl.n_tiles + 1;
@@ -559,6 +596,22 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
     p.mags = io.mags32;
     p.hb_tiles = hb_tiles; p.tile_lo = 0; p.tiles_in_launch = tl.n_tiles;
     float* hb[2] = { (float*)ctx->scratch[S_HB0], (float*)ctx->scratch[S_HB1] };
+    // singular-bin guard: [n_clips] statistic (float bits) | [n_clips] clip scale | [n_clips] selection list | count
+    unsigned int* g_stat = nullptr; float* g_scale = nullptr; int* g_list = nullptr; int* g_count = nullptr;
+    float g_thr = 0.0f;
+    if (redo) {
+        g_stat = (unsigned int*)ctx->scratch[S_GUARD];
+        g_scale = (float*)(g_stat + n_clips);
+        g_list = (int*)(g_scale + n_clips);
+        g_count = g_list + n_clips;
+        CU(cudaMemsetAsync(g_stat, 0, (size_t)n_clips * 4, ctx->st));
+        k_clip_scale<<<(unsigned)n_clips, 128, 0, ctx->st>>>(io.mags32, g_scale, tl.n_frames);
+        ctx->launches++;
+        p.guard_stat = g_stat;
+        // statistic = M/|X| * rms_frame(M) with M pre-scaled by 1/N and |X| not: N * statistic / clip scale is the
+        // leverage in the units of profiles/r02_gl_guard.md
+        g_thr = ctx->gl_guard / (float)geo.n_fft;
+    }
     CU(cudaEventRecord(ctx->ev_k0, ctx->st));
     if (int rc = fork()) return rc;
     for (int i = lead; i < iters; i++) {
@@ -569,8 +622,13 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
         for (int g = 0; g < ns; g++) {
             p.clip0 = c_lo(g);
             const unsigned gg = (unsigned)((long)(c_lo(g + 1) - c_lo(g)) * tl.n_tiles);
-            if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
-            else k_gl_iter<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+            if (redo) {
+                if (geo.alt) k_gl_iter<kAltHS, kAltFS, true><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+                else k_gl_iter<kHS, 16, true><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+            } else {
+                if (geo.alt) k_gl_iter<kAltHS, kAltFS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+                else k_gl_iter<kHS><<<gg, kThreads, kGlSmemBytes, gs[g]>>>(p);
+            }
             ctx->launches++;
         }
         cur32 = dst;
@@ -583,6 +641,45 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
         k_halo_fix<<<(unsigned)(grid - n_clips), 256, 0, ctx->st>>>(io.out32, (const float*)hb[(iters - 1) & 1], tl, geo.hop,
                                                                   geo.halo, 0, 1, hb_tiles, p);
         ctx->launches++;
+    }
+    if (redo) {
+        // The clips the guard selected run the same iterations again in float64, from the float64 signal of the
+        // hand-over, and overwrite their float32 result: they end where GOMEL_FLAG_F64 would.  The selection is made on
+        // the device; the re-run kernels are small fixed grids walking (list slot, tile) items over short tiles, so a
+        // run without selected clips costs a few microseconds per launch and one with a few clips a few pair times
+        // per iteration.
+        d64::k_guard_select<<<1, 1024, 0, ctx->st>>>(g_stat, g_scale, g_thr, n_clips, g_list, g_count);
+        ctx->launches++;
+        const Tiling rt = redo_tiling(tl, geo);
+        const int r_hb_tiles = rt.n_tiles + 1;
+        double* rhb[2] = { (double*)ctx->scratch[S_GHB0], (double*)ctx->scratch[S_GHB1] };
+        d64::GLParams q = {};
+        q.tables = geo.alt ? ctx->d_tables_d64_alt : ctx->d_tables_d64; q.tl = rt; q.mags = redo->mags64;
+        q.hb_tiles = r_hb_tiles; q.tile_lo = 0; q.tiles_in_launch = rt.n_tiles;
+        q.sel.clips = g_list; q.sel.count = g_count;
+        const long items = (long)n_clips * rt.n_tiles, slots = (long)kGlCtasPerSm * ctx->sm_count;
+        const unsigned rgrid = (unsigned)(items < slots ? items : slots);
+        const double* cur = redo->fin;
+        double* dst64[2] = { redo->other, redo->fin };
+        for (int j = 0; j < iters - lead; j++) {
+            q.sig_in = cur; q.sig_out = dst64[j & 1];
+            q.hb_in = (j == 0) ? nullptr : rhb[(j - 1) & 1];
+            q.hb_out = rhb[j & 1];
+            if (geo.alt) d64::k_gl_iter_f64<kAltHS, kAltFS, true><<<rgrid, kThreads, d64::kSmemBytes, ctx->st>>>(q);
+            else d64::k_gl_iter_f64<kHS, 16, true><<<rgrid, kThreads, d64::kSmemBytes, ctx->st>>>(q);
+            ctx->launches++;
+            cur = dst64[j & 1];
+        }
+        double* fin = const_cast<double*>(cur);
+        if (rt.n_tiles > 1) {
+            d64::k_halo_fix_f64<<<rgrid, 256, 0, ctx->st>>>(fin, rhb[(iters - lead - 1) & 1], rt, geo.hop, geo.halo, 1, r_hb_tiles,
+                                                           rt.n_tiles, q.sel);
+            ctx->launches++;
+        }
+        const unsigned gy = (unsigned)(n_clips < 64 ? n_clips : 64);
+        d64::k_f64_to_f32_selected<<<dim3(16, gy), 256, 0, ctx->st>>>(fin, io.out32, geo.ola(tl.n_frames), tl.sig_stride, q.sel);
+        ctx->launches++;
+        ctx->guard_clips = n_clips; ctx->guard_thr_units = g_thr;
     }
     CU(cudaGetLastError());
     return 0;
@@ -795,6 +892,7 @@ int gomel_ctx_create(int device, gomel_ctx** out)
             if (v >= 0) ctx->lead_f64 = v;
         }
         if (const char* e = getenv("GOMEL_F32_TAIL")) ctx->f32_tail = atoi(e) < 0 ? -1 : atoi(e);   // trailing float32 iterations, < 0 unlimited
+        if (const char* e = getenv("GOMEL_GL_GUARD")) { const double v = atof(e); if (v >= 0) ctx->gl_guard = (float)v; }
         std::vector<float> blob;
         build_fft_tables(blob);
         CU(cudaMalloc(&ctx->d_tables, kTableBytes));
@@ -804,6 +902,8 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         CU(cudaMemcpy(ctx->d_tables_alt, blob.data(), kTableBytes, cudaMemcpyHostToDevice));
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kAltHS, MODE_MEL, kAltFS>)) return rc;
         CU(cudaFuncSetAttribute(k_gl_iter<kAltHS, kAltFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
+        CU(cudaFuncSetAttribute(k_gl_iter<kAltHS, kAltFS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
+        CU(cudaFuncSetAttribute(k_gl_iter<kHS, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGlSmemBytes));
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_MEL>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_PHASE>)) return rc;
         if (int rc = set_smem_attr(ctx, k_stft_fwd<kHS, MODE_SPEC>)) return rc;
@@ -855,6 +955,37 @@ int gomel_set_lead_f64(gomel_ctx* ctx, int lead)
     const int prev = ctx->lead_f64;
     ctx->lead_f64 = lead;
     return prev;
+}
+
+int gomel_set_gl_guard(gomel_ctx* ctx, float threshold, float* previous)
+{
+    if (!ctx || !(threshold >= 0.0f)) return GOMEL_E_ARG;
+    Guard g(ctx);
+    if (previous) *previous = ctx->gl_guard;
+    ctx->gl_guard = threshold;
+    return 0;
+}
+
+int gomel_last_gl_guard(gomel_ctx* ctx, int* n_clips, int* n_rerun, float* max_leverage, float* leverage, int cap)
+{
+    if (!ctx || !n_clips || !n_rerun || !max_leverage || (cap > 0 && !leverage)) return GOMEL_E_ARG;
+    Guard g(ctx);
+    *n_clips = ctx->guard_clips; *n_rerun = 0; *max_leverage = 0.0f;
+    if (ctx->guard_clips <= 0) return 0;
+    const int n = ctx->guard_clips;
+    std::vector<float> h((size_t)n * 2);
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaMemcpy(h.data(), ctx->scratch[S_GUARD], (size_t)n * 8, cudaMemcpyDeviceToHost));
+    // guard_thr_units = threshold / N: leverage = statistic / clip scale / guard_thr_units * threshold
+    const float to_lev = ctx->gl_guard > 0 && ctx->guard_thr_units > 0 ? ctx->gl_guard / ctx->guard_thr_units : 0.0f;
+    for (int c = 0; c < n; c++) {
+        const float stat = h[c], scale = h[(size_t)n + c];
+        const float lev = scale > 0 ? stat / scale * to_lev : 0.0f;
+        if (stat > ctx->guard_thr_units * scale) ++*n_rerun;
+        if (lev > *max_leverage) *max_leverage = lev;
+        if (c < cap) leverage[c] = lev;
+    }
+    return 0;
 }
 
 int gomel_set_f32_tail(gomel_ctx* ctx, int tail)

@@ -252,6 +252,39 @@ __device__ __forceinline__ c64 join_hi(c64 ya, c64 yb) { return mk(ya.x + yb.y, 
 
 using gomel::prefetch_l2;
 
+// The clips whose float32 tail is re-run in float64 (see k_gl_iter<.., GUARD>), as a dense list built on the device:
+// the re-run kernels are launched with a small fixed grid and walk (list slot, tile) items, so a run in which the
+// guard selects nothing costs a few microseconds per launch and the host never has to read the count.
+struct Selection {
+    const int* clips;        // [count] clip indices, ascending
+    const int* count;
+};
+// stat = the float32 iterations' per-clip maximum of M/|X| * rms_frame(M) (float bits), scale = the clip's rms
+// magnitude, thr = the threshold in units of the clip scale.  One block; ordered, deterministic.
+__global__ void __launch_bounds__(1024) k_guard_select(const unsigned int* __restrict__ stat, const float* __restrict__ scale,
+                                                       float thr, int n_clips, int* __restrict__ clips, int* __restrict__ count)
+{
+    __shared__ int warp_n[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n_clips; c0 += 1024) {
+        const int c = c0 + threadIdx.x;
+        const bool sel = c < n_clips && __uint_as_float(stat[c]) > thr * scale[c];
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_n[w] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; i++) off += warp_n[i];
+        if (sel) clips[off + __popc(m & ((1u << lane) - 1u))] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; i++) t += warp_n[i]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
 struct GLParams {
     const double* tables;    // T1 | T2 | win  (kTableBytes)
     Tiling tl;
@@ -263,6 +296,7 @@ struct GLParams {
     int hb_tiles, tile_lo, tiles_in_launch;
     int edge_mode, edge_tile0, edge_tile1;
     int ext_prev, ext_next, clip0;
+    Selection sel;           // clips != null: grid-stride walk over (list slot, tile) items; hb buffers are indexed by slot
 };
 
 // One Griffin-Lim iteration (one pass of the loop body of mel.ISTFT, mel/mel.go:85-136) in float64.
@@ -270,10 +304,16 @@ struct GLParams {
 // (its tail), the later tile's to hb_out (its head); every reader adds the two.
 // FS = frame slots (Resolut / 256): 16 is the native frame; 8 (Resolut 2048, the mel.NewMel default) runs the frame
 // zero-extended through the same 4096-point core, its spectrum on the even core bins (cf. k_gl_iter).
-template <int HS, int FS = 16>
+template <int HS, int FS = 16, bool LISTED = false>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool listed = LISTED;
+    int item = blockIdx.x, n_items = 0;
+    if (listed) {                    // re-run of the float32 tail of selected clips: usually nothing to do
+        n_items = *p.sel.count * p.tiles_in_launch;
+        if (item >= n_items) return;
+    }
     const Smem s = carve(smem_raw);
     const Lanes L = make_lanes64();
     {
@@ -282,9 +322,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
         for (int i = L.t; i < kTableBytes / 16; i += kThreads) d[i] = __ldg(g + i);
     }
     constexpr int NR = FS + HS, KEEP = FS - HS, H = 256 * HS, HALO = KEEP * 256;
-    int tile, clip;
-    if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; }
-    else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = p.clip0 + blockIdx.x / p.tiles_in_launch; }
+  for (;;) {                         // one pass unless listed
+    int tile, clip, hslot;
+    if (p.edge_mode) { clip = 0; tile = blockIdx.x == 0 ? p.edge_tile0 : p.edge_tile1; hslot = 0; }
+    else if (listed) { hslot = item / p.tiles_in_launch; tile = p.tile_lo + item % p.tiles_in_launch; clip = p.sel.clips[hslot]; }
+    else { tile = p.tile_lo + blockIdx.x % p.tiles_in_launch; clip = p.clip0 + blockIdx.x / p.tiles_in_launch; hslot = clip; }
     const int f0 = tile_begin(p.tl, tile);
     const int nf = tile_begin(p.tl, tile + 1) - f0;
     const int npairs = (nf + 1) >> 1;
@@ -295,9 +337,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
     const long lim_l = p.tl.sig_len - sbase;
     const int lim = (int)(lim_l < 0x7fffff00L ? lim_l : 0x7fffff00L);
     const bool has_prev = tile > 0 || p.ext_prev, has_next = (tile + 1) < p.tl.n_tiles || p.ext_next;
-    const double* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)clip * p.hb_tiles + tile) * HALO : nullptr;
+    const double* __restrict__ hin_own = p.hb_in ? p.hb_in + ((long)hslot * p.hb_tiles + tile) * HALO : nullptr;
     const double* __restrict__ hin_next = hin_own ? hin_own + HALO : nullptr;
-    double* __restrict__ hout = p.hb_out + ((long)clip * p.hb_tiles + tile) * HALO;
+    double* __restrict__ hout = p.hb_out + ((long)hslot * p.hb_tiles + tile) * HALO;
     const int t = L.t;
 
     auto ld = [&](int row) -> double {
@@ -447,21 +489,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter_f64(const GLParams p)
             }
         }
     }
+    if (!listed) break;
+    item += gridDim.x;
+    if (item >= n_items) break;
+  }
 }
 
 // folds the head partials in: sig[s] += hb[s] over the head regions of tiles t_first .. t_end-1 (t_end = n_tiles, or
 // n_tiles + 1 when slot n_tiles holds the next rank's head partial over this rank's tail region)
 __global__ void k_halo_fix_f64(double* __restrict__ sig, const double* __restrict__ hb, Tiling tl, int hop, int halo,
-                               int t_first, int hb_tiles, int t_end)
+                               int t_first, int hb_tiles, int t_end, Selection sel = Selection{ nullptr, nullptr })
 {
     const int nt = t_end - t_first;
-    const int clip = blockIdx.x / nt, tile = blockIdx.x % nt + t_first;
-    const long s0 = (long)tile_begin(tl, tile) * hop;
-    double* __restrict__ d = sig + (long)clip * tl.sig_stride + s0;
-    const double* __restrict__ h = hb + ((long)clip * hb_tiles + tile) * halo;
-    const long room = tl.sig_len - s0;
-    const int n = (int)(room < halo ? (room < 0 ? 0 : room) : halo);
-    for (int o = threadIdx.x; o < n; o += blockDim.x) d[o] += h[o];
+    const int n_items = sel.clips ? *sel.count * nt : (int)gridDim.x;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int slot = item / nt, tile = item % nt + t_first;
+        const int clip = sel.clips ? sel.clips[slot] : slot;
+        const long s0 = (long)tile_begin(tl, tile) * hop;
+        double* __restrict__ d = sig + (long)clip * tl.sig_stride + s0;
+        const double* __restrict__ h = hb + ((long)slot * hb_tiles + tile) * halo;
+        const long room = tl.sig_len - s0;
+        const int n = (int)(room < halo ? (room < 0 ? 0 : room) : halo);
+        for (int o = threadIdx.x; o < n; o += blockDim.x) d[o] += h[o];
+    }
 }
 
 // rows of `len` valid samples, `stride` apart in both buffers: the gap after each row is not touched
@@ -473,6 +523,18 @@ __global__ void k_f64_to_f32_rows(const double* __restrict__ in, float* __restri
     for (; i < n; i += step) {
         const long r = i / len, o = r * stride + (i - r * len);
         out[o] = (float)in[o];
+    }
+}
+
+// the same for the guard's selected clips only: grid = (chunks, list slots)
+__global__ void k_f64_to_f32_selected(const double* __restrict__ in, float* __restrict__ out, long len, long stride, Selection sel)
+{
+    const int count = *sel.count;
+    for (int slot = blockIdx.y; slot < count; slot += gridDim.y) {
+        const int clip = sel.clips[slot];
+        const double* a = in + (long)clip * stride;
+        float* b = out + (long)clip * stride;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long)gridDim.x * blockDim.x) b[i] = (float)a[i];
     }
 }
 

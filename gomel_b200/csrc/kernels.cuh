@@ -14,6 +14,7 @@
 namespace gomel {
 
 constexpr int kMagStride = 2052;     // floats per magnitude row: 2049 bins, 16-byte aligned rows
+constexpr int kMagRmsCell = 2049;    // first pad cell of a row: the frame's rms magnitude (k_mags_from_mel)
 
 // position of bin k = k0 + 16*k1 + 256*k2 inside a magnitude row: k2*256 + rho(k0)*16 + k1 with
 // rho = rotate-left-by-1 of the 4-bit k0.  The digit-reversed spectrum layout of fft4096_fwd then
@@ -393,6 +394,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                                                        double tune_add, double tune_mul, long n_rows)
 {
     extern __shared__ double e[];     // [kMagsRowsPerPass][n_mels][2]
+    __shared__ double red[8][kMagsRowsPerPass];
     const int per_row = 2 * n_mels;
     // (v - TuneAdd) / TuneMul / N as one multiplication: exact for the default TuneMul = 1, otherwise within one
     // float64 ulp of the reference's division, far below the float32 rounding of the stored magnitude
@@ -403,6 +405,9 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
         __syncthreads();
         for (int i = threadIdx.x; i < nr * per_row; i += blockDim.x) e[i] = exp((double)m[i]);
         __syncthreads();
+        double ss[kMagsRowsPerPass];
+#pragma unroll
+        for (int r = 0; r < kMagsRowsPerPass; r++) ss[r] = 0.0;
         for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes in mag_pos order
             const int kc = mag_unpos(pos);
             if (FS == 8 && (kc & 1)) {
@@ -413,7 +418,9 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
             const int lo = inv_lo[i], hi = inv_hi[i];
             const bool copy = lo == hi, lerp = (lo + 1 == hi) && hi < n_mels;
             const double md = lerp ? inv_mod[i] : 0.0;
-            for (int r = 0; r < nr; r++) {
+#pragma unroll
+            for (int r = 0; r < kMagsRowsPerPass; r++) {
+                if (r >= nr) break;
                 const double* er = e + r * per_row;
                 OUT* out = mags + (row0 + r) * kMagStride;
                 const int nch = (i == FS * 128 - 1) ? 2 : 1;
@@ -431,10 +438,40 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                                          ? fabs((total - tune_add) / tune_mul) * (1.0 / (256.0 * FS))
                                          : fabs((total - tune_add) * scale);
                     out[l ? 2048 : pos] = (OUT)v;
+                    ss[r] += v * v;
                 }
             }
         }
+        // the frame's rms target magnitude goes to the row's first pad cell (kMagRmsCell): the scale of the
+        // float32 iterations' singular-bin guard (k_gl_iter<.., GUARD>); fixed reduction order, deterministic
+#pragma unroll
+        for (int r = 0; r < kMagsRowsPerPass; r++) {
+            double v = ss[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][r] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            double v = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][threadIdx.x];
+            mags[(row0 + threadIdx.x) * kMagStride + kMagRmsCell] = (OUT)sqrt(v * (1.0 / 2049.0));
+        }
     }
+}
+
+// rms of a clip's frame rms values (fixed order): the clip-level scale of the singular-bin guard
+__global__ void __launch_bounds__(128) k_clip_scale(const float* __restrict__ mags, float* __restrict__ scale, long n_frames)
+{
+    __shared__ float red[4];
+    const float* m = mags + (long)blockIdx.x * n_frames * kMagStride + kMagRmsCell;
+    float v = 0.0f;
+    for (long f = threadIdx.x; f < n_frames; f += blockDim.x) { const float x = m[f * kMagStride]; v = fmaf(x, x, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) scale[blockIdx.x] = sqrtf((red[0] + red[1] + red[2] + red[3]) / (float)n_frames);
 }
 
 // ------------------------------------------------------------------ shared pieces of the synthesis kernels
@@ -461,6 +498,8 @@ struct SynParams {
     // phase ISTFT of one rank's slice of a long clip: the window-sum gain is a function of the GLOBAL sample index
     long gain_off;           // global index of local sample 0 (a multiple of the hop); 0 = whole clip here
     long total_len;          // length of the whole clip's signal
+    // k_gl_iter<.., GUARD = true>: per-clip running maximum of the singular-bin statistic (float bits, atomicMax)
+    unsigned int* guard_stat;
 };
 
 __device__ __forceinline__ float rsqrt_fast(float x)       // one MUFU.RSQ; callers guarantee x >= 1e-36 (no denormal path)
@@ -469,13 +508,20 @@ __device__ __forceinline__ float rsqrt_fast(float x)       // one MUFU.RSQ; call
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float2 subst_phase(float2 X, float M)
+__device__ __forceinline__ float max3(float a, float b, float c)     // one FMNMX3
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float2 subst_phase(float2 X, float M, float* ratio = nullptr)
 {
     // cmplx.Rect(M, cmplx.Phase(X)) = M * X/|X|, and Phase(0) = 0 -> (M, 0)   (mel/mel.go:98-102).
     // Branch-free: Y = (X + (d,0)) * M / sqrt(|X|^2 + d^2) with d = 1e-18.  For X = 0 this is exactly the
     // reference's (M, 0); for any X the transforms can produce (|X| >> 1e-10) d is far below one ulp.
     const float n = fmaf(X.x, X.x, fmaf(X.y, X.y, 1e-36f));
     const float r = M * rsqrt_fast(n);
+    if (ratio) *ratio = r;                         // M / |X| for the guard
     float2 y = __fmul2_rn(X, make_float2(r, r));
     y.x = fmaf(1e-18f, r, y.x);
     return y;
@@ -491,7 +537,13 @@ __device__ __forceinline__ float2 subst_phase(float2 X, float M)
 constexpr int kGlMagBytes = 2 * kMagStride * 4;                 // two magnitude rows (frames A and B)
 constexpr int kGlSmemBytes = kSmemBytes + kGlMagBytes + 16 + 256;   // + one mbarrier + the special coset's scratch
 
-template <int HS, int FS = 16>
+// GUARD: the singular-bin guard.  A float32 iteration decides the phase of a bin from a value with an absolute error
+// of ~1e-7 of the frame's rms bin; where |X[k]| is that small while the target M[k] is not, the float32 and float64
+// trajectories take different branches (profiles/r02_gl_guard.md).  The kernel records, per clip, the maximum over
+// bins and frames of  M[k]/|X[k]| * rms(M of the frame)  -- the error a unit absolute perturbation of that bin
+// injects, up to the clip's scale; the host side re-runs the float32 tail of the clips above a threshold in float64.
+// Cost: one FMNMX per bin on the ALU pipe.
+template <int HS, int FS = 16, bool GUARD = false>
 __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -555,6 +607,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
 #pragma unroll
     for (int m = 0; m < FS; m++) win[m] = win_at<FS>(s.win, m, t);
 
+    float gmax = 0.0f;
     for (int pr = 0; pr < npairs; pr++) {
         const int off0 = pr * 2 * H;
         const bool validB = (f0 + 2 * pr + 1) < p.tl.n_frames;
@@ -612,14 +665,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                 __syncwarp();
             }
             float2 nlo[8], nhi[8];               // results go to fresh registers: no in-place ordering constraints
+            float ra = 0.0f, rb = 0.0f, qa[2], qb[2];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float ma = mA[j * 256];
                 const float mb = validB ? mB[j * 256] : 0.0f;
                 const float2 P = shfl2(v[15 - j], L.src);
                 const float2 z = v[j];
-                const float2 ya = subst_phase(split_a(z, P), ma);
-                const float2 yb = subst_phase(split_b(z, P), mb);
+                const float2 ya = subst_phase(split_a(z, P), ma, GUARD ? &qa[j & 1] : nullptr);
+                const float2 yb = subst_phase(split_b(z, P), mb, GUARD ? &qb[j & 1] : nullptr);
+                if (GUARD && (j & 1)) { ra = max3(ra, qa[0], qa[1]); rb = max3(rb, qb[0], qb[1]); }
                 nlo[j] = join_lo(ya, yb);
                 nhi[j] = shfl2(join_hi(ya, yb), L.src);
             }
@@ -632,8 +687,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                     const float ma = smag[mi];
                     const float mb = validB ? smag[kMagStride + mi] : 0.0f;
                     const float2 z = zsc[j], P = zsc[jp];
-                    const float2 ya = subst_phase(split_a(z, P), ma);
-                    const float2 yb = subst_phase(split_b(z, P), mb);
+                    const float2 ya = subst_phase(split_a(z, P), ma, GUARD ? &qa[0] : nullptr);
+                    const float2 yb = subst_phase(split_b(z, P), mb, GUARD ? &qb[0] : nullptr);
+                    if (GUARD) { ra = fmaxf(ra, qa[0]); rb = fmaxf(rb, qb[0]); }
                     zsc[16 + j] = join_lo(ya, yb);
                     if (jp != j) zsc[16 + jp] = join_hi(ya, yb);
                 }
@@ -643,6 +699,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
                     for (int i = 0; i < 16; i++) v[i] = zsc[16 + i];
                 }
             }
+            if (GUARD) gmax = fmaxf(gmax, fmaxf(ra * smag[kMagRmsCell], rb * smag[kMagStride + kMagRmsCell]));
         }
 
         fft4096_inv(v, s, L);
@@ -667,6 +724,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gl_iter(const SynParams p)
     }
 #pragma unroll
     for (int j = 0; j < KEEP; j++) st(npairs * 2 * H + j * 256, acc[j]);
+    if (GUARD) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if ((t & 31) == 0 && gmax > 0.0f) atomicMax(p.guard_stat + clip, __float_as_uint(gmax));     // non-negative floats order like their bits
+    }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -87,6 +87,19 @@ int  gomel_set_tile_frames(gomel_ctx *ctx, int tile_frames);
  * is the all-float32 loop of round 1.  Each returns the previous value (unlimited tail: INT_MAX). */
 int  gomel_set_lead_f64(gomel_ctx *ctx, int lead_iters);
 int  gomel_set_f32_tail(gomel_ctx *ctx, int f32_tail);
+/* Singular-bin guard of the float32 tail.  A float32 iteration decides the phase of every bin from a value that
+ * carries an absolute error of ~1e-7 of the frame's rms bin; when |X[k]| is that small while the target M[k] is not,
+ * the float32 and float64 trajectories take different branches and end ~1e-4 apart -- about one (clip, start signal)
+ * pair in 10,000 under the 16 + 16 policy (profiles/r02_gl_guard.md).  The float32 kernel therefore records, per
+ * clip, the largest  leverage = M[k]/|X[k]| * rms_frame(M)/rms_clip(M)  it meets; clips above `threshold` have
+ * their float32 iterations run again in float64 from the float64 signal of the hand-over, so that they end exactly
+ * where GOMEL_FLAG_F64 ends.  Default 5e4 (env GOMEL_GL_GUARD): the one pair in 10,560 that missed 1e-4 had 1.3e6,
+ * and the worst error a bin of leverage L can inject is about 2e-10 L; 0.5 % of clips are re-run.  0 disables.  Not applied when no float64 lead iteration ran (lead_iters = 0) or on the
+ * time-split sessions. */
+int  gomel_set_gl_guard(gomel_ctx *ctx, float threshold, float *previous);
+/* the guard's record of the last Griffin-Lim call on this context (blocks until it has finished): clips seen
+ * (0: the guard did not run), clips re-run in float64, the largest leverage, and the first `cap` clips' leverage */
+int  gomel_last_gl_guard(gomel_ctx *ctx, int *n_clips, int *n_rerun, float *max_leverage, float *leverage, int cap);
 
 /* ---- sizing: pad (mel/impl.go:429-455) + gossp NumFrames + ISTFT length (mel/mel.go:79) --- */
 int  gomel_frames(const gomel_config *cfg, long n_samples, long *n_padded, long *n_frames, long *ola_len);

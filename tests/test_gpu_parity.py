@@ -712,11 +712,94 @@ def test_gl_precision_policy_on_the_known_hard_start_signals(mctx, oracle):
         assert err < TOL_GL / 4, (clip, seed, err)
         for lead in (4, 12):
             prev = mctx.set_gl_precision(lead, -1)
+            prev_guard = mctx.set_gl_guard(0.0)          # the bare split: the guard would re-run some of these
             try:
                 short_fails += rel_l2(m.FromMel(mel.copy()), exact) > TOL_GL
             finally:
                 mctx.set_gl_precision(*prev)
+                mctx.set_gl_guard(prev_guard)
     assert short_fails >= 3
+
+
+def test_gl_guard_reruns_the_known_singular_pair(mctx, oracle):
+    """clip0 / start signal 10338 (found by the 10,560-pair sweep, profiles/r02_gl_guard.md): at iteration 17 one bin
+    with a sizeable target magnitude has an analysis value ~1e-6 of the frame's rms bin, the float32 tail resolves its
+    phase differently from float64 and ends 2.7e-4 away.  The guard must see it (leverage ~1.3e6, threshold 5e4),
+    re-run the tail in float64 and end at the float64 result; an ordinary pair must not be touched."""
+    mel = oracle.to_mel(oracle.config(), synth_clip(0, 10.0))
+    for seed, singular in ((10338, True), (20000, False)):
+        init = np.random.default_rng(seed).random(440576)
+        m = _mel_obj(32, True)
+        m.InitSignal = init
+        exact = m.FromMel(mel.copy())
+        m = _mel_obj(32, False)
+        m.InitSignal = init
+        got = m.FromMel(mel.copy())
+        n, rerun, lev, per = mctx.last_gl_guard(cap=1)
+        assert n == 1 and per[0] == lev
+        prev = mctx.set_gl_guard(0.0)
+        try:
+            bare = m.FromMel(mel.copy())
+            assert mctx.last_gl_guard()[0] == 0             # guard off: nothing recorded
+        finally:
+            assert mctx.set_gl_guard(prev) == 0.0
+        if singular:
+            assert lev > 2e5 and rerun == 1, (lev, rerun)
+            assert rel_l2(got, exact) < 2e-7, rel_l2(got, exact)       # the float64 result, narrowed to float32
+            print(f"singular pair: leverage {lev:.3e}, guard off {rel_l2(bare, exact):.2e}, guard on {rel_l2(got, exact):.2e}")
+        else:
+            assert lev < 5e4 and rerun == 0, (lev, rerun)
+            assert np.array_equal(got, bare)
+            assert rel_l2(got, exact) < TOL_GL / 10
+
+
+def test_gl_guard_in_a_batch_touches_only_the_selected_clips(mctx, lib, oracle):
+    """a low threshold selects part of a batch: selected clips end at the all-float64 result, the others are bit-identical
+    to the run without the guard; both chunked host call and device call; several tilings"""
+    from gomel_b200 import _lib
+    cfg = mel_cfg(lib, iters=20)                              # 16 float64 + 4 float32
+    n_clips = 12
+    wavs = [synth_clip(60 + c, 1.9) for c in range(n_clips)]
+    mels = [oracle.to_mel(oracle.config(), w).astype(np.float32) for w in wavs]
+    frames = len(mels[0]) // 192
+    mel32 = np.stack([m_.reshape(-1) for m_ in mels])
+    ola = 4096 + (frames - 1) * 1280
+    init32 = np.random.default_rng(4).random((n_clips, ola), dtype=np.float32)
+    cfg64 = lib.make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=20, flags=_lib.FLAG_F64)
+
+    def batch(chunk):
+        out = np.empty((n_clips, ola), np.float32)
+        mctx.check(mctx.lib.gomel_from_mel_batch_host(
+            mctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), n_clips, frames,
+            init32.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_void_p), chunk))
+        return out
+
+    for tile in (0, 6):
+        mctx.set_tile_frames(tile)
+        try:
+            prev = mctx.set_gl_guard(0.0)
+            bare = batch(n_clips)
+            mctx.set_gl_guard(1e30)
+            batch(n_clips)
+            _, _, _, lev = mctx.last_gl_guard(cap=n_clips)
+            thr = float(np.median(lev))                      # about half of the clips
+            mctx.set_gl_guard(thr)
+            got = batch(n_clips)
+            n, rerun, mx, lev2 = mctx.last_gl_guard(cap=n_clips)
+            assert n == n_clips and np.array_equal(lev, lev2) and mx == lev.max()
+            sel = lev > thr
+            assert rerun == int(sel.sum()) and 0 < rerun < n_clips
+            got5 = batch(5)                                  # chunks of 5, 5, 2: same selection, same results
+            assert np.array_equal(got5, got)
+        finally:
+            mctx.set_gl_guard(prev)
+            mctx.set_tile_frames(0)
+        for c in range(n_clips):
+            if sel[c]:
+                exact = mctx.from_mel(cfg64, mel32[c].astype(np.float64).reshape(-1, 2), init=init32[c].astype(np.float64))
+                assert rel_l2(got[c], exact) < 2e-7, (tile, c, rel_l2(got[c], exact))
+            else:
+                assert np.array_equal(got[c], bare[c]), (tile, c)
 
 
 def test_gl_precision_knobs(mctx, oracle):

@@ -27,6 +27,13 @@ imp = np.zeros(n)
 imp[rng.integers(0, n, max(4, n // 11000))] = rng.uniform(-1, 1, max(4, n // 11000))
 kinds.append(("impulses", imp))
 rows = []
+from gomel_b200 import _lib                                  # noqa: E402
+ctx = _lib.default_context(0)
+guard_mode = os.environ.get("GL_SWEEP_GUARD", "default")     # "record": statistic only, nothing re-run; "off"; "default"
+if guard_mode == "record":
+    ctx.set_gl_guard(1e30)
+elif guard_mode == "off":
+    ctx.set_gl_guard(0.0)
 for name, wav in kinds:
     mel = O.to_mel(O.config(), wav)
     frames = len(mel) // 192
@@ -34,12 +41,15 @@ for name, wav in kinds:
     errs = []
     for s in range(n_seeds):
         init = np.random.default_rng(seed0 + s).random(ola)
-        e = rel_l2(run(mel, init, iters, False), run(mel, init, iters, True))
+        hyb = run(mel, init, iters, False)
+        _, n_rerun, lev, _ = ctx.last_gl_guard()
+        e = rel_l2(hyb, run(mel, init, iters, True))
         errs.append(e)
-        rows.append({"clip": name, "iters": iters, "seed": seed0 + s, "rel_l2": e})
+        rows.append({"clip": name, "iters": iters, "seed": seed0 + s, "rel_l2": e, "leverage": lev, "rerun": n_rerun})
     print(f"GL-{iters} {seconds:g}s {name}: max {max(errs):.2e} median {np.median(errs):.2e}", flush=True)
 v = np.array([r["rel_l2"] for r in rows])
 summ = {"iters": iters, "seconds": seconds, "pairs": int(len(v)), "max": float(v.max()), "median": float(np.median(v)),
-        "p99": float(np.quantile(v, 0.99)), "pass_frac_1e-4": float(np.mean(v <= 1e-4)), "misses": int(np.sum(v > 1e-4))}
+        "p99": float(np.quantile(v, 0.99)), "pass_frac_1e-4": float(np.mean(v <= 1e-4)), "misses": int(np.sum(v > 1e-4)),
+        "guard": guard_mode, "rerun_frac": float(np.mean([r["rerun"] for r in rows]))}
 print(json.dumps(summ))
-json.dump({"rows": rows, "summary": summ}, open(os.path.join(ROOT, "gpurun_out", f"gl_policy_sweep_{iters}_{seed0}_{seconds:g}.json"), "w"), indent=1)
+json.dump({"rows": rows, "summary": summ}, open(os.path.join(ROOT, "gpurun_out", f"gl_policy_sweep_{iters}_{seed0}_{seconds:g}_{guard_mode}.json"), "w"), indent=1)
