@@ -412,7 +412,7 @@ def parity_record(ctx, cfg, _lib, base_mel, frames, ola, n=4):
         errs32.append(float(np.linalg.norm(out32[c] - exact) / d))
     return {"what": f"{nb} bench clips, benchmarked call vs all-float64 fused kernel (GOMEL_FLAG_F64), same float32 inputs",
             "rel_l2": errs, "rel_l2_max": max(errs), "tolerance": 1e-4, "all_float32_rel_l2": errs32,
-            "sweep": "profiles/r02_gl_parity_sweep.md (1,056 pairs at 32 iterations and 96 at 100: none outside 1e-4 under the default policy)"}
+            "sweep": "profiles/r02_gl_parity_sweep.md, r02_gl_guard.md (10,560 + 2,112 pairs at 32 iterations, 1,056 at 100: none outside 1e-4 under the default policy with its guard; max 2.4e-5)"}
 
 
 def run_product(args):
@@ -498,6 +498,7 @@ def run_product(args):
     t_wall1 = time.time()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
+    g_n, g_rerun, g_max, _ = ctx.last_gl_guard()        # the last timed step's singular-bin guard record
 
     # ---- end-to-end timing through the host-buffer C ABI call
     for w in range(max(1, min(args.warmup, 2))):
@@ -534,8 +535,9 @@ def run_product(args):
     modes = {}
     cfg_f64 = _lib.make_config(n_fft=N_FFT, hop=HOP, n_mels=N_MELS, n_freqs=768, gl_iters=GL_ITERS, flags=_lib.FLAG_F64)
     for name, c, prec in ((("all_float32", cfg, (0, -1)), ("lead4_float64_then_float32", cfg, (4, -1)),
-                           ("all_float64", cfg_f64, None)) if args.modes else ()):
+                           ("default_split_without_guard", cfg, None), ("all_float64", cfg_f64, None)) if args.modes else ()):
         prev = ctx.set_gl_precision(*prec) if prec else None
+        prev_guard = ctx.set_gl_guard(0.0) if name != "all_float64" else None      # the bare splits
         step_device(1, c=c)
         barrier()
         ctx.timer_start()
@@ -543,11 +545,15 @@ def run_product(args):
         ms = ctx.timer_stop()
         if prev:
             ctx.set_gl_precision(*prev)
+        if prev_guard is not None:
+            ctx.set_gl_guard(prev_guard)
         barrier()
         ms = reduce_max([ms])[0]
         modes[name] = {"ms_per_step": ms, "value": world * clips * frames * HOP / SR / (ms / 1e3),
-                       "misses_1e-4_in_1056_pair_sweep": {"all_float32": "3 % (29 % at 100 iterations)", "lead4_float64_then_float32": "0.9 %",
-                                                          "all_float64": "0"}[name]}
+                       "misses_1e-4": {"all_float32": "3 % of 1,056 pairs (29 % at 100 iterations)",
+                                       "lead4_float64_then_float32": "0.9 % of 1,056 pairs",
+                                       "default_split_without_guard": "1 of 10,560 pairs (0 of the first 2,112)",
+                                       "all_float64": "0"}[name]}
 
     # ---- strong scaling of configs[3]: 1024 clips in TOTAL, 1024 / N per rank (device-resident and end to end)
     strong = None
@@ -679,8 +685,11 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic", "config": workload_config(n_gpus),
-            "precision": {"policy": "lead = max(16, iters - 16) Griffin-Lim iterations in float64 (k_gl_iter_f64), the rest in float32 (k_gl_iter)",
+            "precision": {"policy": "lead = max(16, iters - 16) Griffin-Lim iterations in float64 (k_gl_iter_f64), the rest in float32 (k_gl_iter); "
+                                    "clips whose float32 iterations meet a near-singular bin (leverage > 5e4) have them re-run in float64 "
+                                    "(profiles/r02_gl_guard.md: 10,560 of 10,560 pairs within 1e-4)",
                           "float64_iterations": lead_it, "float32_iterations": (GL_ITERS - lead_it) if lead_it is not None else None,
+                          "guard": {"threshold": 5e4, "clips_seen_last_step": g_n, "clips_rerun_last_step": g_rerun, "max_leverage_last_step": g_max},
                           "other_modes_device_resident": modes},
             "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

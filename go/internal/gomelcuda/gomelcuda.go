@@ -231,6 +231,20 @@ func (x *Ctx) SetGLPrecision(lead, tail int) {
 	C.gomel_set_f32_tail(x.h, C.int(tail))
 }
 
+// SetGLGuard sets the leverage threshold of the float32 tail's singular-bin guard (library default 5e4; 0 disables):
+// clips whose float32 iterations meet a bin with M/|X| that large have those iterations re-run in float64.
+func (x *Ctx) SetGLGuard(threshold float32) error {
+	return x.err(C.gomel_set_gl_guard(x.h, C.float(threshold), nil))
+}
+
+// LastGLGuard reports the guard's record of the last Griffin-Lim call: clips seen, clips re-run, largest leverage.
+func (x *Ctx) LastGLGuard() (seen, rerun int, maxLeverage float32, err error) {
+	var n, r C.int
+	var m C.float
+	rc := C.gomel_last_gl_guard(x.h, &n, &r, &m, nil, 0)
+	return int(n), int(r), float32(m), x.err(rc)
+}
+
 func (x *Ctx) Image(buf [][2]float64, mels int) ([]uint16, error) {
 	if mels <= 0 || len(buf) < mels {
 		return nil, errors.New("gomel: fewer entries than one column")

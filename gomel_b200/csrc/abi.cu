@@ -63,6 +63,7 @@ constexpr int kDefaultF32Tail = 16;
 // Singular-bin guard of the float32 tail (profiles/r02_gl_guard.md): clips whose statistic exceeds this many clip-rms
 // units have their tail re-run in float64.  0 disables.
 constexpr float kDefaultGlGuard = 5.0e4f;
+constexpr int kGuardSyncClips = 4;
 
 }  // namespace
 
@@ -82,6 +83,7 @@ struct gomel_ctx {
     int lead_f64 = kDefaultLeadF64;   // gomel_set_lead_f64 / GOMEL_LEAD_F64
     int f32_tail = kDefaultF32Tail;   // gomel_set_f32_tail / GOMEL_F32_TAIL; < 0: unlimited
     float gl_guard = kDefaultGlGuard; // gomel_set_gl_guard / GOMEL_GL_GUARD
+    int* h_guard_count = nullptr;     // pinned: the selection count of a small call (read back instead of launching blind)
     int guard_clips = 0;              // clips of the last guarded Griffin-Lim run (statistics in scratch[S_GUARD]); 0: none
     float guard_thr_units = 0;        // the threshold that run used, in statistic units
     double* d_tables_d64 = nullptr;   // gl_f64.cuh tables (built on first use)
@@ -650,6 +652,14 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
         // per iteration.
         d64::k_guard_select<<<1, 1024, 0, ctx->st>>>(g_stat, g_scale, g_thr, n_clips, g_list, g_count);
         ctx->launches++;
+        ctx->guard_clips = n_clips; ctx->guard_thr_units = g_thr;
+        // A call on a few clips is latency bound (the single-clip drop-in call): reading the count back costs one
+        // stream synchronisation, the 18 blind launches cost more.  Large batches stay asynchronous.
+        if (n_clips <= kGuardSyncClips) {
+            CU(cudaMemcpyAsync(ctx->h_guard_count, g_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+            if (*ctx->h_guard_count == 0) { CU(cudaGetLastError()); return 0; }
+        }
         const Tiling rt = redo_tiling(tl, geo);
         const int r_hb_tiles = rt.n_tiles + 1;
         double* rhb[2] = { (double*)ctx->scratch[S_GHB0], (double*)ctx->scratch[S_GHB1] };
@@ -679,7 +689,6 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
         const unsigned gy = (unsigned)(n_clips < 64 ? n_clips : 64);
         d64::k_f64_to_f32_selected<<<dim3(16, gy), 256, 0, ctx->st>>>(fin, io.out32, geo.ola(tl.n_frames), tl.sig_stride, q.sel);
         ctx->launches++;
-        ctx->guard_clips = n_clips; ctx->guard_thr_units = g_thr;
     }
     CU(cudaGetLastError());
     return 0;
@@ -887,6 +896,7 @@ int gomel_ctx_create(int device, gomel_ctx** out)
         CU(cudaEventCreate(&ctx->ev_k1));
         CU(cudaEventCreate(&ctx->ev_l0));
         CU(cudaEventCreate(&ctx->ev_l1));
+        CU(cudaMallocHost(&ctx->h_guard_count, sizeof(int)));
         if (const char* e = getenv("GOMEL_LEAD_F64")) {             // float64 lead iterations, >= 0
             const int v = atoi(e);
             if (v >= 0) ctx->lead_f64 = v;
@@ -928,6 +938,7 @@ void gomel_ctx_destroy(gomel_ctx* ctx)
     cudaFree(ctx->d_tables64);
     cudaFree(ctx->d_tables_d64); cudaFree(ctx->d_tables_d64_alt);
     cudaEventDestroy(ctx->ev_l0); cudaEventDestroy(ctx->ev_l1);
+    cudaFreeHost(ctx->h_guard_count);
     for (MelTables& t : ctx->mel_tabs) t.release();
     cudaFree(ctx->d_gain_head); cudaFree(ctx->d_gain_mid); cudaFree(ctx->d_gain_tail);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
