@@ -64,6 +64,7 @@ constexpr int kDefaultF32Tail = 16;
 // units have their tail re-run in float64.  0 disables.
 constexpr float kDefaultGlGuard = 5.0e4f;
 constexpr int kGuardSyncClips = 4;
+constexpr int kGuardRefFrames = 342;
 
 }  // namespace
 
@@ -86,6 +87,7 @@ struct gomel_ctx {
     int* h_guard_count = nullptr;     // pinned: the selection count of a small call (read back instead of launching blind)
     int guard_clips = 0;              // clips of the last guarded Griffin-Lim run (statistics in scratch[S_GUARD]); 0: none
     float guard_thr_units = 0;        // the threshold that run used, in statistic units
+    float guard_to_leverage = 0;      // statistic / clip scale -> leverage, for that run
     double* d_tables_d64 = nullptr;   // gl_f64.cuh tables (built on first use)
     double* d_tables_d64_alt = nullptr;   // same twiddles, Hann window of the 2048-sample frame
     float4* d_tables = nullptr;
@@ -612,7 +614,9 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
         p.guard_stat = g_stat;
         // statistic = M/|X| * rms_frame(M) with M pre-scaled by 1/N and |X| not: N * statistic / clip scale is the
         // leverage in the units of profiles/r02_gl_guard.md
-        g_thr = ctx->gl_guard / (float)geo.n_fft;
+        // The threshold is stated for a clip of kGuardRefFrames frames (the 10 s clips it was calibrated on): one bin's
+        // share of a clip's norm falls with the square root of the frame count.
+        g_thr = ctx->gl_guard * std::sqrt((float)tl.n_frames / (float)kGuardRefFrames) / (float)geo.n_fft;
     }
     CU(cudaEventRecord(ctx->ev_k0, ctx->st));
     if (int rc = fork()) return rc;
@@ -652,7 +656,7 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
         // per iteration.
         d64::k_guard_select<<<1, 1024, 0, ctx->st>>>(g_stat, g_scale, g_thr, n_clips, g_list, g_count);
         ctx->launches++;
-        ctx->guard_clips = n_clips; ctx->guard_thr_units = g_thr;
+        ctx->guard_clips = n_clips; ctx->guard_thr_units = g_thr; ctx->guard_to_leverage = (float)geo.n_fft;
         // A call on a few clips is latency bound (the single-clip drop-in call): reading the count back costs one
         // stream synchronisation, the 18 blind launches cost more.  Large batches stay asynchronous.
         if (n_clips <= kGuardSyncClips) {
@@ -987,8 +991,7 @@ int gomel_last_gl_guard(gomel_ctx* ctx, int* n_clips, int* n_rerun, float* max_l
     std::vector<float> h((size_t)n * 2);
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaMemcpy(h.data(), ctx->scratch[S_GUARD], (size_t)n * 8, cudaMemcpyDeviceToHost));
-    // guard_thr_units = threshold / N: leverage = statistic / clip scale / guard_thr_units * threshold
-    const float to_lev = ctx->gl_guard > 0 && ctx->guard_thr_units > 0 ? ctx->gl_guard / ctx->guard_thr_units : 0.0f;
+    const float to_lev = ctx->guard_to_leverage;     // statistic / clip scale -> leverage (the transform length)
     for (int c = 0; c < n; c++) {
         const float stat = h[c], scale = h[(size_t)n + c];
         const float lev = scale > 0 ? stat / scale * to_lev : 0.0f;

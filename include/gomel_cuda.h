@@ -94,7 +94,9 @@ int  gomel_set_f32_tail(gomel_ctx *ctx, int f32_tail);
  * clip, the largest  leverage = M[k]/|X[k]| * rms_frame(M)/rms_clip(M)  it meets; clips above `threshold` have
  * their float32 iterations run again in float64 from the float64 signal of the hand-over, so that they end exactly
  * where GOMEL_FLAG_F64 ends.  Default 5e4 (env GOMEL_GL_GUARD): the one pair in 10,560 that missed 1e-4 had 1.3e6,
- * and the worst error a bin of leverage L can inject is about 2e-10 L; 0.5 % of clips are re-run.  0 disables.  Not applied when no float64 lead iteration ran (lead_iters = 0) or on the
+ * and the worst error a bin of leverage L can inject is about 2e-10 L; 0.5 % of clips are re-run.  0 disables.
+ * The threshold is stated for 342-frame (10 s) clips and scaled by sqrt(frames / 342) inside: one bin's share of a
+ * clip's norm falls with the square root of the frame count.  Not applied when no float64 lead iteration ran (lead_iters = 0) or on the
  * time-split sessions. */
 int  gomel_set_gl_guard(gomel_ctx *ctx, float threshold, float *previous);
 /* the guard's record of the last Griffin-Lim call on this context (blocks until it has finished): clips seen

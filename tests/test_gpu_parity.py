@@ -783,7 +783,7 @@ def test_gl_guard_in_a_batch_touches_only_the_selected_clips(mctx, lib, oracle):
             batch(n_clips)
             _, _, _, lev = mctx.last_gl_guard(cap=n_clips)
             thr = float(np.median(lev))                      # about half of the clips
-            mctx.set_gl_guard(thr)
+            mctx.set_gl_guard(thr / np.sqrt(frames / 342.0))  # the knob is stated for 342-frame clips
             got = batch(n_clips)
             n, rerun, mx, lev2 = mctx.last_gl_guard(cap=n_clips)
             assert n == n_clips and np.array_equal(lev, lev2) and mx == lev.max()
