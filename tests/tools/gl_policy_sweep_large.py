@@ -34,6 +34,10 @@ if guard_mode == "record":
     ctx.set_gl_guard(1e30)
 elif guard_mode == "off":
     ctx.set_gl_guard(0.0)
+if "GL_SWEEP_LEAD" in os.environ:                             # a split other than the default: lead L, the rest float32
+    ctx.set_gl_precision(int(os.environ["GL_SWEEP_LEAD"]), -1)
+if "GL_SWEEP_THR" in os.environ:
+    ctx.set_gl_guard(float(os.environ["GL_SWEEP_THR"]))
 for name, wav in kinds:
     mel = O.to_mel(O.config(), wav)
     frames = len(mel) // 192
@@ -52,4 +56,4 @@ summ = {"iters": iters, "seconds": seconds, "pairs": int(len(v)), "max": float(v
         "p99": float(np.quantile(v, 0.99)), "pass_frac_1e-4": float(np.mean(v <= 1e-4)), "misses": int(np.sum(v > 1e-4)),
         "guard": guard_mode, "rerun_frac": float(np.mean([r["rerun"] for r in rows]))}
 print(json.dumps(summ))
-json.dump({"rows": rows, "summary": summ}, open(os.path.join(ROOT, "gpurun_out", f"gl_policy_sweep_{iters}_{seed0}_{seconds:g}_{guard_mode}.json"), "w"), indent=1)
+json.dump({"rows": rows, "summary": summ}, open(os.path.join(ROOT, "gpurun_out", f"gl_policy_sweep_{iters}_{seed0}_{seconds:g}_{guard_mode}" + ("_lead" + os.environ["GL_SWEEP_LEAD"] if "GL_SWEEP_LEAD" in os.environ else "") + ".json"), "w"), indent=1)
