@@ -98,6 +98,41 @@ def test_from_mel_defaults_float64_matches_oracle(ctx, oracle, restore_tables, s
     ctx.set_tile_frames(0)
 
 
+@pytest.mark.parametrize("tile", [0, 10])
+def test_gl_guard_on_the_defaults_geometry(ctx, oracle, restore_tables, tile):
+    """the float32 tail's singular-bin guard on Resolut 2048 / Window 256: with the threshold under the clip's leverage the
+    float32 iterations are re-run in float64 and the call ends at the GOMEL_FLAG_F64 result; above it nothing changes"""
+    wav = synth_clip(24, 1.3)
+    ocfg = _ocfg(oracle, 20)
+    mel = oracle.to_mel(ocfg, wav)
+    frames = len(mel) // 160
+    init = np.random.default_rng(7003).random(2048 + (frames - 1) * 256)
+
+    def run(strict):
+        m = _newmel(20)
+        m.Strict = strict
+        m.InitSignal = init
+        return m.FromMel(mel.copy())
+
+    ctx.set_tile_frames(tile)
+    prev = ctx.set_gl_guard(0.0)
+    try:
+        exact, bare = run(True), run(False)
+        assert ctx.last_gl_guard()[0] == 0
+        ctx.set_gl_guard(1e30)
+        assert np.array_equal(run(False), bare)
+        n, rerun, lev, _ = ctx.last_gl_guard()
+        assert n == 1 and rerun == 0 and lev > 0
+        ctx.set_gl_guard(lev / 2 / np.sqrt(frames / 342.0))
+        got = run(False)
+        assert ctx.last_gl_guard()[1] == 1
+        assert rel_l2(got, exact) < 2e-7, rel_l2(got, exact)
+        assert 0 < rel_l2(bare, exact) < TOL_GL
+    finally:
+        ctx.set_gl_guard(prev)
+        ctx.set_tile_frames(0)
+
+
 @pytest.mark.parametrize("frames", [1, 2, 3, 7, 8, 9, 15, 16, 17])
 def test_from_mel_defaults_tiny_frame_counts(ctx, oracle, restore_tables, frames):
     rng = np.random.default_rng(frames)
