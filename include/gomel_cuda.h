@@ -99,8 +99,9 @@ int  gomel_set_f32_tail(gomel_ctx *ctx, int f32_tail);
  * clip's norm falls with the square root of the frame count.  Not applied when no float64 lead iteration ran (lead_iters = 0) or on the
  * time-split sessions. */
 int  gomel_set_gl_guard(gomel_ctx *ctx, float threshold, float *previous);
-/* the guard's record of the last Griffin-Lim call on this context (blocks until it has finished): clips seen
- * (0: the guard did not run), clips re-run in float64, the largest leverage, and the first `cap` clips' leverage */
+/* the guard's record of the last Griffin-Lim call on this context -- for the chunked *_batch_host calls, of their last
+ * chunk -- (blocks until it has finished): clips seen (0: the guard did not run), clips re-run in float64, the largest
+ * leverage, and the first `cap` clips' leverage */
 int  gomel_last_gl_guard(gomel_ctx *ctx, int *n_clips, int *n_rerun, float *max_leverage, float *leverage, int cap);
 
 /* ---- sizing: pad (mel/impl.go:429-455) + gossp NumFrames + ISTFT length (mel/mel.go:79) --- */
