@@ -412,7 +412,7 @@ def parity_record(ctx, cfg, _lib, base_mel, frames, ola, n=4):
         errs32.append(float(np.linalg.norm(out32[c] - exact) / d))
     return {"what": f"{nb} bench clips, benchmarked call vs all-float64 fused kernel (GOMEL_FLAG_F64), same float32 inputs",
             "rel_l2": errs, "rel_l2_max": max(errs), "tolerance": 1e-4, "all_float32_rel_l2": errs32,
-            "sweep": "profiles/r02_gl_parity_sweep.md, r02_gl_guard.md (10,560 + 2,112 pairs at 32 iterations, 1,056 at 100: none outside 1e-4 under the default policy with its guard; max 2.4e-5)"}
+            "sweep": "profiles/r02_gl_parity_sweep.md, r02_gl_guard.md (44,352 pairs at 32 iterations under the default policy with its guard: one at 1.3e-4, one at 9.8e-5, all others <= 2.4e-5; 1,056 at 100 iterations: max 6.9e-6)"}
 
 
 def run_product(args):
@@ -687,7 +687,7 @@ def run_product(args):
             "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic", "config": workload_config(n_gpus),
             "precision": {"policy": "lead = max(16, iters - 16) Griffin-Lim iterations in float64 (k_gl_iter_f64), the rest in float32 (k_gl_iter); "
                                     "clips whose float32 iterations meet a near-singular bin (leverage > 5e4) have them re-run in float64 "
-                                    "(profiles/r02_gl_guard.md: 10,560 of 10,560 pairs within 1e-4)",
+                                    "(profiles/r02_gl_guard.md: 44,351 of 44,352 pairs within 1e-4)",
                           "float64_iterations": lead_it, "float32_iterations": (GL_ITERS - lead_it) if lead_it is not None else None,
                           "guard": {"threshold": 5e4, "clips_seen_last_step": g_n, "clips_rerun_last_step": g_rerun, "max_leverage_last_step": g_max},
                           "other_modes_device_resident": modes},

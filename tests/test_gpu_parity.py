@@ -753,6 +753,33 @@ def test_gl_guard_reruns_the_known_singular_pair(mctx, oracle):
             assert rel_l2(got, exact) < TOL_GL / 10
 
 
+def test_gl_known_transient_instability_pair(mctx, oracle):
+    """The one pair of 42,240 that the default policy leaves outside the tolerance (profiles/r02_gl_guard.md): the sweep's
+    impulse clip with start signal 30888.  No bin is singular (leverage 8e2); the float32 / float64 deviation grows ~3.5x per
+    iteration from iteration 26 on (a transient instability of the iteration itself) and reaches 1.3e-4 at 32.  Recorded
+    here so that it stays visible: the default must stay below 2e-4 on it, and a float32 tail of 8 iterations
+    (gomel_set_f32_tail(8): 10,560 / 10,560 pairs of the same population within 1.5e-5) must bring it under 2e-5."""
+    n = 441000
+    rng = np.random.default_rng(8)
+    wav = np.zeros(n)
+    wav[rng.integers(0, n, max(4, n // 11000))] = rng.uniform(-1, 1, max(4, n // 11000))
+    mel = oracle.to_mel(oracle.config(), wav)
+    init = np.random.default_rng(30888).random(440576)
+    m = _mel_obj(32, True)
+    m.InitSignal = init
+    exact = m.FromMel(mel.copy())
+    m = _mel_obj(32, False)
+    m.InitSignal = init
+    err = rel_l2(m.FromMel(mel.copy()), exact)
+    prev = mctx.set_f32_tail(8)
+    try:
+        err8 = rel_l2(m.FromMel(mel.copy()), exact)
+    finally:
+        mctx.set_f32_tail(prev)
+    print(f"transient-instability pair: default {err:.2e}, float32 tail of 8: {err8:.2e}")
+    assert err < 2e-4 and err8 < 2e-5, (err, err8)
+
+
 def test_gl_guard_in_a_batch_touches_only_the_selected_clips(mctx, lib, oracle):
     """a low threshold selects part of a batch: selected clips end at the all-float64 result, the others are bit-identical
     to the run without the guard; both chunked host call and device call; several tilings"""
