@@ -61,7 +61,11 @@ typedef struct {
  * outcome by 1e-4 .. 1e-3.  Measured on 1,056 (clip, start signal) pairs at 32 iterations
  * (profiles/r02_gl_parity_sweep.md): an all-float32 loop misses the 1e-4 tolerance on 3 % of the pairs, 4 float64
  * lead iterations on 0.9 %, 12 on 0.1 %, 16 on none (worst 1.3e-5); on flat spectra float32 errors also grow in
- * late bursts, so long float32 tails are unsafe at 100 iterations.  Default policy: the first `lead` iterations run
+ * late bursts, so long float32 tails are unsafe at 100 iterations.  (Later sweeps of 42,240 more pairs under the
+ * default policy, profiles/r02_gl_guard.md: one pair at 2.7e-4 from a near-singular bin in the float32 tail -- now
+ * re-run in float64 by the guard, gomel_set_gl_guard below -- and one at 1.3e-4 from a transient instability of the
+ * iteration that only a shorter float32 tail removes: gomel_set_f32_tail(ctx, 8) holds all 10,560 pairs of that
+ * population within 1.5e-5 at 15 % less throughput.)  Default policy: the first `lead` iterations run
  * in float64 end to end on the fused kernel of gl_f64.cuh, the rest in float32, with
  * lead = max(16, GriffinLimIterations - 16) -- at least sixteen float64 iterations first, at most sixteen float32
  * ones last (runs of <= 16 iterations are float64 throughout).  See gomel_set_lead_f64 / gomel_set_f32_tail.
