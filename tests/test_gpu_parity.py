@@ -865,6 +865,31 @@ def test_from_mel_tiny_frame_counts(mctx, oracle, frames):
     assert got.shape == ref.shape and rel_l2(got, ref) < TOL_GL
 
 
+@pytest.mark.parametrize("frames", [1, 2, 3, 5, 8, 9])
+@pytest.mark.parametrize("iters", [17, 19])
+def test_from_mel_tiny_frame_counts_across_the_hand_over(mctx, oracle, frames, iters):
+    """the same with a float32 tail (16 float64 + 1 or 3 float32 iterations), guard off / recording / forced to re-run:
+    the hand-over, the guard's statistic and its short-tile re-run all have to cope with clips of a frame or two"""
+    rng = np.random.default_rng(100 + frames)
+    mel = rng.uniform(-9.0, 3.0, (frames * 192, 2))
+    init = rng.random(4096 + (frames - 1) * 1280)
+    ref = oracle.from_mel(oracle.config(gl_iters=iters), mel, init)
+    prev = mctx.set_gl_guard(0.0)
+    try:
+        for thr, want_rerun in ((0.0, None), (1e30, 0), (1e-30, 1)):
+            mctx.set_gl_guard(thr)
+            m = _mel_obj(iters, False)
+            m.InitSignal = init
+            got = m.FromMel(mel.copy())
+            assert got.shape == ref.shape and rel_l2(got, ref) < TOL_GL, (thr, rel_l2(got, ref))
+            if want_rerun is not None:
+                assert mctx.last_gl_guard()[:2] == (1, want_rerun)
+            if want_rerun:
+                assert rel_l2(got, ref) < 2e-7              # re-run: the float64 result
+    finally:
+        mctx.set_gl_guard(prev)
+
+
 def test_from_mel_tune_parameters(mctx, oracle):
     """TuneMul / TuneAdd of Mel.undospectrum (mel/impl.go:386-408), incl. the Abs() of a negative result"""
     mel = oracle.to_mel(oracle.config(), synth_clip(16, 0.4))
