@@ -865,6 +865,43 @@ def test_from_mel_tiny_frame_counts(mctx, oracle, frames):
     assert got.shape == ref.shape and rel_l2(got, ref) < TOL_GL
 
 
+def test_gl_guard_rerun_of_every_clip_of_a_batch(mctx, lib, oracle):
+    """threshold ~0: the whole batch (1500 clips -- more than one selection pass of 1024, two stream groups, chunks of
+    600) goes through the list-driven float64 re-run; sampled clips must equal the all-float64 result"""
+    from gomel_b200 import _lib
+    cfg = mel_cfg(lib, iters=18)
+    n_clips = 1500
+    base = [oracle.to_mel(oracle.config(), synth_clip(80 + c, 0.35)).astype(np.float32).reshape(-1) for c in range(5)]
+    frames = len(base[0]) // (192 * 2)
+    mel32 = np.stack([base[c % 5] for c in range(n_clips)])
+    ola = 4096 + (frames - 1) * 1280
+    init32 = np.random.default_rng(6).random((n_clips, ola), dtype=np.float32)
+    out = np.empty((n_clips, ola), np.float32)
+    prev = mctx.set_gl_guard(1e-30)
+    try:
+        mctx.check(mctx.lib.gomel_from_mel_batch_host(
+            mctx.h, C.byref(cfg), mel32.ctypes.data_as(C.c_void_p), n_clips, frames,
+            init32.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_void_p), 600))
+        n, rerun, _, _ = mctx.last_gl_guard()
+        assert n == rerun and 0 < n <= 600                   # the last chunk
+        d_mel, d_init, d_out = mctx.dev_malloc(mel32.nbytes), mctx.dev_malloc(init32.nbytes), mctx.dev_malloc(out.nbytes)
+        mctx.h2d(d_mel, mel32)
+        mctx.h2d(d_init, init32)
+        mctx.check(mctx.lib.gomel_from_mel_dev(mctx.h, C.byref(cfg), d_mel, n_clips, frames, d_init, 0, ola, d_out))
+        dev = np.empty_like(out)
+        mctx.d2h(dev, d_out)
+        for p in (d_mel, d_init, d_out):
+            mctx.dev_free(p)
+        assert mctx.last_gl_guard()[:2] == (n_clips, n_clips)
+    finally:
+        mctx.set_gl_guard(prev)
+    cfg64 = lib.make_config(n_fft=4096, hop=1280, n_mels=192, n_freqs=768, gl_iters=18, flags=_lib.FLAG_F64)
+    for c in (0, 1, 599, 600, 1023, 1024, 1499):
+        exact = mctx.from_mel(cfg64, mel32[c].astype(np.float64).reshape(-1, 2), init=init32[c].astype(np.float64))
+        assert rel_l2(out[c], exact) < 2e-7, (c, rel_l2(out[c], exact))
+        assert rel_l2(dev[c], exact) < 2e-7, (c, rel_l2(dev[c], exact))
+
+
 @pytest.mark.parametrize("frames", [1, 2, 3, 5, 8, 9])
 @pytest.mark.parametrize("iters", [17, 19])
 def test_from_mel_tiny_frame_counts_across_the_hand_over(mctx, oracle, frames, iters):
