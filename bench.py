@@ -625,7 +625,7 @@ def run_product(args):
                     lead_traffic = tj["lead_kernel"]["dram_bytes_per_frame_iter"] * clips * frames
                 except Exception:
                     pass
-            f32_rec = {"bound": "hbm", "kernel": "k_gl_iter<5, 16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            f32_rec = {"bound": "hbm", "kernel": "k_gl_iter<5, 16, GUARD>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame-iteration of one --set full capture "
                                          "of this build (profiles/gl_iter_traffic.json) x the frame-iterations of one launch",
