@@ -699,7 +699,8 @@ int gl_dev_f32(gomel_ctx* ctx, const gomel_config* cfg, const Geo& geo, const Gl
 }
 
 template <typename T, typename OUT>
-int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, OUT* d_mags, cudaStream_t stream = nullptr)
+int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_rows, OUT* d_mags, cudaStream_t stream = nullptr,
+             float* d_mags_f32 = nullptr)         // OUT = double: also the float32 rows, in the same pass
 {
     if (!stream) stream = ctx->st;
     const MelTables* mt = find_mel_tables(ctx, cfg);
@@ -710,10 +711,10 @@ int mags_dev(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_row
     const size_t sm = (size_t)kMagsRowsPerPass * cfg->n_mels * 2 * sizeof(double);
     if (cfg->n_fft == 256 * kAltFS)
         k_mags_from_mel<T, kAltFS, OUT><<<(unsigned)g, 256, sm, stream>>>(
-            d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+            d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows, d_mags_f32);
     else
         k_mags_from_mel<T, 16, OUT><<<(unsigned)g, 256, sm, stream>>>(
-            d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows);
+            d_mel, d_mags, mt->inv_lo, mt->inv_hi, mt->inv_mod, cfg->n_mels, cfg->tune_add, cfg->tune_mul, n_rows, d_mags_f32);
     ctx->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -727,17 +728,17 @@ int mags_for_gl(gomel_ctx* ctx, const gomel_config* cfg, const T* d_mel, long n_
     Geo geo;
     if (int rc = check_cfg(ctx, cfg, &geo)) return rc;
     const int lead = lead_iters(ctx, cfg, geo);
-    void* m;
-    if (cfg->gl_iters - lead > 0) {
-        if (int rc = ensure(ctx, slot32, (size_t)n_rows * kMagStride * 4, &m)) return rc;
-        if (int rc = mags_dev<T, float>(ctx, cfg, d_mel, n_rows, (float*)m, stream)) return rc;
-        io->mags32 = (const float*)m;
+    void *m32 = nullptr, *m64 = nullptr;
+    const bool need32 = cfg->gl_iters - lead > 0, need64 = lead > 0;
+    if (need32) { if (int rc = ensure(ctx, slot32, (size_t)n_rows * kMagStride * 4, &m32)) return rc; }
+    if (need64) { if (int rc = ensure(ctx, slot64, (size_t)n_rows * kMagStride * 8, &m64)) return rc; }
+    if (need64) {         // one pass writes both precisions when both are needed
+        if (int rc = mags_dev<T, double>(ctx, cfg, d_mel, n_rows, (double*)m64, stream, (float*)m32)) return rc;
+    } else if (need32) {
+        if (int rc = mags_dev<T, float>(ctx, cfg, d_mel, n_rows, (float*)m32, stream)) return rc;
     }
-    if (lead > 0) {
-        if (int rc = ensure(ctx, slot64, (size_t)n_rows * kMagStride * 8, &m)) return rc;
-        if (int rc = mags_dev<T, double>(ctx, cfg, d_mel, n_rows, (double*)m, stream)) return rc;
-        io->mags64 = (const double*)m;
-    }
+    io->mags32 = (const float*)m32;
+    io->mags64 = (const double*)m64;
     return 0;
 }
 
@@ -1503,8 +1504,14 @@ static int from_mel_batch_host_impl(gomel_ctx* ctx, const gomel_config* cfg, con
         if (c >= kPipeSets) CH(cudaStreamWaitEvent(ctx->st_pre, ev.done[b], 0));    // chunk c-3 no longer reads dmags[b] / dinit[b]
         if (!chain.ok()) break;
         GlIO io;
-        if (need32) { rc = mags_dev<float, float>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (float*)dm32[b], ctx->st_pre); io.mags32 = (const float*)dm32[b]; }
-        if (!rc && need64) { rc = mags_dev<float, double>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (double*)dm64[b], ctx->st_pre); io.mags64 = (const double*)dm64[b]; }
+        if (need64) {         // one pass writes both precisions when both are needed
+            rc = mags_dev<float, double>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (double*)dm64[b], ctx->st_pre,
+                                         need32 ? (float*)dm32[b] : nullptr);
+            io.mags64 = (const double*)dm64[b];
+        } else if (need32) {
+            rc = mags_dev<float, float>(ctx, cfg, (const float*)dmel[b], (long)nc * n_frames, (float*)dm32[b], ctx->st_pre);
+        }
+        if (need32) io.mags32 = (const float*)dm32[b];
         if (!rc && !init) {
             // indexed by the sample's position in the whole batch: the start signals do not depend on the chunking
             // and equal those of gomel_from_mel_dev(seed) on the same batch

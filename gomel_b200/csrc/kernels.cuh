@@ -391,8 +391,12 @@ template <typename T, int FS = 16, typename OUT = float>
 __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel, OUT* __restrict__ mags,
                                                        const int* __restrict__ inv_lo, const int* __restrict__ inv_hi,
                                                        const double* __restrict__ inv_mod, int n_mels,
-                                                       double tune_add, double tune_mul, long n_rows)
+                                                       double tune_add, double tune_mul, long n_rows,
+                                                       float* __restrict__ mags_f32 = nullptr)
 {
+    // mags_f32 (OUT = double only): the float32 rows of the same frames, written in the same pass -- a Griffin-Lim run
+    // under the precision policy needs both, and the second pass over the mel rows was 0.5 % of the bench step
+    const bool dual = std::is_same<OUT, double>::value && mags_f32 != nullptr;
     extern __shared__ double e[];     // [kMagsRowsPerPass][n_mels][2]
     __shared__ double red[8][kMagsRowsPerPass];
     const int per_row = 2 * n_mels;
@@ -411,7 +415,10 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
         for (int pos = threadIdx.x; pos < 2048; pos += blockDim.x) {      // unit-stride writes in mag_pos order
             const int kc = mag_unpos(pos);
             if (FS == 8 && (kc & 1)) {
-                for (int r = 0; r < nr; r++) mags[(row0 + r) * kMagStride + pos] = (OUT)0;
+                for (int r = 0; r < nr; r++) {
+                    mags[(row0 + r) * kMagStride + pos] = (OUT)0;
+                    if (dual) mags_f32[(row0 + r) * kMagStride + pos] = 0.0f;
+                }
                 continue;
             }
             const int i = kc >> (FS == 16 ? 0 : 1);
@@ -434,10 +441,14 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
                         for (int k = lo; k < hi; k++) total += er[2 * k + l];
                         total /= (double)(hi - lo + 1);
                     }
-                    const double v = std::is_same<OUT, double>::value
-                                         ? fabs((total - tune_add) / tune_mul) * (1.0 / (256.0 * FS))
-                                         : fabs((total - tune_add) * scale);
+                    double v = std::is_same<OUT, double>::value
+                                   ? fabs((total - tune_add) / tune_mul) * (1.0 / (256.0 * FS))
+                                   : fabs((total - tune_add) * scale);
                     out[l ? 2048 : pos] = (OUT)v;
+                    if (dual) {          // exactly the value the OUT = float instantiation stores
+                        v = fabs((total - tune_add) * scale);
+                        mags_f32[(row0 + r) * kMagStride + (l ? 2048 : pos)] = (float)v;
+                    }
                     ss[r] += v * v;
                 }
             }
@@ -456,6 +467,7 @@ __global__ void __launch_bounds__(256) k_mags_from_mel(const T* __restrict__ mel
             double v = 0.0;
             for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][threadIdx.x];
             mags[(row0 + threadIdx.x) * kMagStride + kMagRmsCell] = (OUT)sqrt(v * (1.0 / 2049.0));
+            if (dual) mags_f32[(row0 + threadIdx.x) * kMagStride + kMagRmsCell] = (float)sqrt(v * (1.0 / 2049.0));
         }
     }
 }
